@@ -1,0 +1,217 @@
+/* teochat_b200 — C-ABI of the B200-native TEOChat inference hot path.
+ *
+ * The reference (ermongroup/TEOChat) has no FFI: its hot path is Python calling
+ * transformers==4.31 / PyTorch.  This header is the boundary a maintainer binds
+ * instead (ctypes stub in INTEGRATION.md): every entry point names the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `host`; tensors are dense row-major;
+ *     bf16 = 16-bit brain float; `stream` is a cudaStream_t passed as void*.
+ *   - calls only enqueue work on `stream` (async w.r.t. the host); the caller synchronises.
+ *   - nothing here allocates or frees caller memory: scratch is passed in, sized by the
+ *     matching `*_workspace_bytes` query.
+ *   - return value: TEO_OK (0) or a negative TEO_ERR_*; text via teo_last_error() (thread-local).
+ *   - a handle is bound to one device and one host thread (one process per GPU).
+ */
+#ifndef TEOCHAT_B200_H_
+#define TEOCHAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEO_OK 0
+#define TEO_ERR_BAD_ARG (-1)
+#define TEO_ERR_CUDA (-2)
+#define TEO_ERR_WORKSPACE (-3)
+#define TEO_ERR_UNSUPPORTED (-4)
+
+#define TEO_ACT_NONE 0
+#define TEO_ACT_QUICK_GELU 1 /* x*sigmoid(1.702x): CLIP default, configuration_image.py:191 */
+#define TEO_ACT_GELU 2       /* erf GELU: nn.GELU(), multimodal_projector/builder.py:44 */
+
+#define TEO_IMAGE_TOKEN_INDEX (-200) /* videollava/constants.py:9 */
+
+typedef struct teo_handle teo_handle;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int teo_create(int device_id, teo_handle** out);
+int teo_destroy(teo_handle* h);
+const char* teo_last_error(void);
+int teo_abi_version(void);
+/* kernels launched through this handle so far (bench.py's gpu_launches) */
+unsigned long long teo_launch_count(const teo_handle* h);
+
+/* ---- synthetic ("random-init") parameters ---------------------------------------------- */
+/* value_i = mean + (sum of the four u16 fields of splitmix64(seed + (i+1)*golden) - 131070) * scale;
+ * replaces the initialisers at languagebind/image/modeling_image.py:179-230 and HF Llama
+ * _init_weights with a device-reproducible stream.  out: bf16 [n]. */
+int teo_init_normal_hash_bf16(void* out, size_t n, uint64_t seed, float scale, float mean, void* stream);
+int teo_init_normal_hash_f32(void* out, size_t n, uint64_t seed, float scale, float mean, void* stream);
+/* out: u8 [n] = top byte of splitmix64(seed + (i+1)*golden) — synthetic frames */
+int teo_init_u8_hash(void* out, size_t n, uint64_t seed, void* stream);
+
+/* ---- GEMM core ------------------------------------------------------------------------- */
+/* C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]) + residual[M,N]   (nn.Linear semantics; replaces the
+ * cuBLAS calls under every nn.Linear of HF CLIPAttention/CLIPMLP (modeling_image.py:11-12),
+ * the projector (multimodal_projector/builder.py:41-48) and HF LlamaAttention/LlamaMLP/lm_head
+ * (llava_llama.py:48,88)).  A, W, bias, residual bf16; fp32 accumulation in TMEM; C bf16, or
+ * fp32 when out_fp32 != 0.  lda/ldw/ldc/ldr in elements; K % 8 == 0, N % 8 == 0, lda % 8 == 0.
+ * bias / residual may be NULL.  residual may alias C. */
+size_t teo_gemm_workspace_bytes(int M, int N, int K);
+int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N,
+                  int K, const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---- vision tower pieces --------------------------------------------------------------- */
+/* ToTensor+Normalize (processing_image.py:18,22) fused with im2col for the 14x14/14 patch conv
+ * (HF CLIPVisionEmbeddings.patch_embedding): frames u8 [n,H,W,3] NHWC → patches bf16 [n*g*g, kpad],
+ * column (c*P+ky)*P+kx, columns >= 3*P*P zero. */
+int teo_patchify_u8_nhwc(const void* frames_u8, void* patches, int n_frames, int image, int patch, int kpad,
+                         void* stream);
+/* same for already-normalised float frames f32 [n,3,H,W] (the reference's pixel_values,
+ * eval/inference.py:52-53) */
+int teo_patchify_f32_nchw(const void* pixel_values, void* patches, int n_frames, int image, int patch, int kpad,
+                          void* stream);
+/* [CLS; patches] + position_embedding → pre_layrnorm (modeling_image.py:645-649):
+ * patch_out bf16 [n*np, d] → hidden bf16 [n*(np+1), d] */
+int teo_vit_assemble_preln(const void* patch_out, const void* cls, const void* pos, const void* ln_w,
+                           const void* ln_b, void* hidden, int n_frames, int n_patches, int d, float eps,
+                           void* stream);
+/* LayerNorm over the last dim (bf16 in/out, fp32 statistics) */
+int teo_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int d, float eps, void* stream);
+/* drop CLS (languagebind/__init__.py:123-124): hidden [n,(np+1),d] → feats [n,np,d] */
+int teo_vit_drop_cls(const void* hidden, void* feats, int n_frames, int n_patches, int d, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------- */
+/* Variable-length multi-head attention, softmax(scale·QK^T [+causal mask])·V, flash-style
+ * (replaces HF CLIPAttention's bmm/softmax/bmm and HF LlamaAttention's prefill branch).
+ * q/k/v: bf16, token-major, row strides ldq/ldk/ldv elements, head h at column h*head_dim;
+ * sequence b owns rows [cu_seqlens[b], cu_seqlens[b+1]).  out: bf16 [tokens, ldo].
+ * head_dim ∈ {64, 128}.  cu_seqlens: int32 [n_seqs+1] on device. */
+int teo_flash_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                        const void* cu_seqlens, int n_seqs, int max_seqlen, int n_heads, int head_dim, float scale,
+                        int causal, void* stream);
+
+/* KV pages: one pool per layer, bf16 [n_pages][2 (K,V)][n_heads][page_size][head_dim]
+ * (replaces HF's torch.cat KV growth).  block_table int32 [n_seqs, max_pages]. */
+/* RoPE (rotate-half, HF LlamaRotaryEmbedding) on q and k in place inside a fused qkv buffer
+ * bf16 [tokens, 3*n_heads*head_dim], then scatter k,v rows into the pages.
+ * positions int32 [tokens]; seq_ids int32 [tokens] (row of block_table; NULL → token index).
+ * rope_cos / rope_sin: f32 [max_pos, head_dim/2] tables built on the host like HF's cos_cached /
+ * sin_cached (so angles are bit-identical to the PyTorch formula). */
+int teo_rope_kv_write(void* qkv, const void* positions, const void* seq_ids, void* kv_pages, const void* block_table,
+                      int max_pages, int tokens, int n_heads, int head_dim, int page_size, const void* rope_cos,
+                      const void* rope_sin, void* stream);
+/* One-token-per-sequence attention over the paged cache (HF LlamaAttention decode branch).
+ * q: bf16 [n_seqs, n_heads*head_dim] (row stride ldq); seq_lens int32 [n_seqs] = cached tokens
+ * including the current one; out bf16 [n_seqs, n_heads*head_dim]. */
+size_t teo_decode_attention_workspace_bytes(int n_seqs, int n_heads, int head_dim, int max_splits);
+int teo_decode_attention(const void* q, int ldq, const void* kv_pages, const void* block_table, int max_pages,
+                         const void* seq_lens, void* out, int n_seqs, int n_heads, int head_dim, int page_size,
+                         int max_seq_len, float scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- LLaMA pieces ---------------------------------------------------------------------- */
+/* y = x * rsqrt(mean(x^2)+eps) * w  (HF LlamaRMSNorm; fp32 statistics, one bf16 rounding) */
+int teo_rmsnorm(const void* x, const void* w, void* y, int rows, int d, float eps, void* stream);
+/* out[r, i] = silu(gate_up[r, i]) * gate_up[r, inter + i]  (HF LlamaMLP act_fn(gate)*up) */
+int teo_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream);
+/* the multimodal splice (llava_arch.py:251-293) as a gather: for flattened token row t,
+ * src[t] >= 0 → embed_tokens[src[t]]; src[t] < 0 → image_feats[-(src[t]+1)] (row of the
+ * [n_images*tokens_per_image, d] projector output).  src int32 [tokens]. */
+int teo_splice_embed(const void* embed_tokens, const void* image_feats, const void* src, void* out, int tokens, int d,
+                     void* stream);
+/* greedy step (HF greedy_search: argmax(logits[:, -1]); first index wins ties) + the eval
+ * path's stopping rule (mm_utils.py:73-104 with keywords ["</s>"] ≡ last id == eos):
+ * logits f32 [n_seqs, vocab]; finished u8 [n_seqs] (in/out); tokens int32 [n_seqs, max_new];
+ * step = column to write; next_ids int32 [n_seqs] (eos for finished rows). */
+int teo_argmax_step(const void* logits, int vocab, void* finished, void* tokens, int max_new, int step,
+                    void* next_ids, int n_seqs, int eos_id, void* stream);
+
+/* ---- whole-model entry points ---------------------------------------------------------- */
+typedef struct {
+    const void *ln1_w, *ln1_b;   /* [d] */
+    const void *qkv_w, *qkv_b;   /* [3d, d], [3d]  (q;k;v rows stacked) */
+    const void *out_w, *out_b;   /* [d, d], [d] */
+    const void *ln2_w, *ln2_b;   /* [d] */
+    const void *fc1_w, *fc1_b;   /* [inter, d], [inter] */
+    const void *fc2_w, *fc2_b;   /* [d, inter], [d] */
+} teo_vit_layer;
+
+typedef struct {
+    int hidden, inter, heads, image, patch, kpad, act, layers_run;
+    float eps;
+    const void* patch_w;         /* [hidden, kpad] bf16, columns (c*P+ky)*P+kx, zero padded */
+    const void *cls, *pos;       /* [hidden], [np+1, hidden] */
+    const void *pre_ln_w, *pre_ln_b;
+    const teo_vit_layer* layers; /* HOST array [layers_run] */
+} teo_vit_model;
+
+/* CLIPVisionTransformer.forward up to hidden_states[select_layer] + feature_select
+ * (modeling_image.py:610-672, languagebind/__init__.py:121-146).  Exactly one of frames_u8
+ * (u8 NHWC) / pixel_values (f32 NCHW, already normalised) is non-NULL.
+ * feats: bf16 [n_frames, np, hidden] (CLS dropped). */
+size_t teo_vit_workspace_bytes(const teo_vit_model* m, int n_frames);
+int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void* frames_u8, const void* pixel_values,
+                   int n_frames, void* feats, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+    int in_dim, hidden;
+    const void *w0, *b0; /* [hidden, in_dim], [hidden] */
+    const void *w2, *b2; /* [hidden, hidden], [hidden] */
+} teo_projector;
+/* mlp2x_gelu (multimodal_projector/builder.py:41-48): feats [rows,in_dim] → out [rows,hidden] */
+size_t teo_projector_workspace_bytes(const teo_projector* p, int rows);
+int teo_projector_mlp2x(teo_handle* h, const teo_projector* p, const void* feats, int rows, void* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+typedef struct {
+    const void* in_norm;    /* [h] */
+    const void* qkv_w;      /* [3h, h] (q;k;v) */
+    const void* o_w;        /* [h, h] */
+    const void* post_norm;  /* [h] */
+    const void* gate_up_w;  /* [2*inter, h] (gate rows then up rows) */
+    const void* down_w;     /* [h, inter] */
+    void* kv_pages;         /* this layer's page pool */
+} teo_llama_layer;
+
+typedef struct {
+    int hidden, inter, heads, layers, vocab, page_size, rope_max_pos;
+    float eps;
+    const void *rope_cos, *rope_sin; /* f32 [rope_max_pos, head_dim/2] */
+    const void* embed;      /* [vocab, h] */
+    const void* final_norm; /* [h] */
+    const void* lm_head;    /* [vocab, h] */
+    const teo_llama_layer* layer; /* HOST array [layers] */
+} teo_llama_model;
+
+/* Ragged batched prefill (HF LlamaModel.forward over inputs_embeds, llava_llama.py:88-99) that
+ * writes K/V into the pages and returns only last-position logits f32 [n_seqs, vocab].
+ * x: bf16 [tokens, h] spliced embeddings (overwritten: used as the residual stream);
+ * cu_seqlens int32 [n_seqs+1]; positions/seq_ids int32 [tokens]; last_rows int32 [n_seqs]. */
+size_t teo_llama_prefill_workspace_bytes(const teo_llama_model* m, int tokens, int n_seqs);
+int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* x, int tokens, const void* cu_seqlens,
+                      const void* positions, const void* seq_ids, const void* last_rows, int n_seqs, int max_seqlen,
+                      const void* block_table, int max_pages, void* logits, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* One greedy decode step for n_seqs sequences (HF generate loop body, SURVEY.md §3.2 hot loop
+ * #1): embed next_ids → 32 layers over the paged cache → logits → argmax/eos.  All state lives
+ * on the device so the step can be captured in a CUDA graph:
+ *   next_ids int32 [n_seqs] (in: token to feed; out: token produced)
+ *   seq_lens int32 [n_seqs] (in: cached length before this step; out: +1)
+ *   finished u8 [n_seqs], tokens int32 [n_seqs, max_new], step_ptr int32 [1] (column, +1). */
+size_t teo_llama_decode_workspace_bytes(const teo_llama_model* m, int n_seqs, int max_seq_len);
+int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, void* next_ids, void* seq_lens, void* finished,
+                          void* tokens, int max_new, void* step_ptr, int n_seqs, int max_seq_len,
+                          const void* block_table, int max_pages, void* logits, int eos_id, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEOCHAT_B200_H_ */

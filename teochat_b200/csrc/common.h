@@ -1,0 +1,101 @@
+// Host-side shared declarations for the C-ABI implementation (internal; the public surface is
+// include/teochat_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+
+#include "../../include/teochat_b200.h"
+
+namespace teo {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+
+#define TEO_CHECK_ARG(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::teo::set_error(__VA_ARGS__);  \
+            return TEO_ERR_BAD_ARG;         \
+        }                                   \
+    } while (0)
+
+#define TEO_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ::teo::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return TEO_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define TEO_LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            ::teo::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));        \
+            return TEO_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define TEO_TRY(call)              \
+    do {                           \
+        int r__ = (call);          \
+        if (r__ != TEO_OK) return r__; \
+    } while (0)
+
+struct TmapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uint64_t>(k.ptr);
+        h = h * 0x9E3779B97F4A7C15ULL ^ k.rows;
+        h = h * 0x9E3779B97F4A7C15ULL ^ k.cols;
+        h = h * 0x9E3779B97F4A7C15ULL ^ k.ld;
+        h = h * 0x9E3779B97F4A7C15ULL ^ k.box_rows;
+        return static_cast<size_t>(h);
+    }
+};
+
+}  // namespace teo
+
+// The opaque per-device handle of the C-ABI.
+struct teo_handle {
+    int device = 0;
+    int num_sms = 148;
+    unsigned long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
+    std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
+};
+
+namespace teo {
+
+// Row-major bf16 matrix [rows, cols] with leading dimension ld (elements) → TMA descriptor with
+// a {64 cols, box_rows} box under SWIZZLE_128B (cached per handle).
+int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  const CUtensorMap** out);
+
+struct GemmEpilogue {
+    const bf16* bias = nullptr;       // [N]
+    const bf16* residual = nullptr;   // [M, ldr]
+    int ldr = 0;
+    int act = TEO_ACT_NONE;
+    int out_fp32 = 0;                 // C is float instead of bf16
+};
+
+// C[M,N] = epilogue(A[M,K] · W[N,K]^T).  Chooses the swap-AB / split-K schedule for small M.
+// workspace: teo_gemm_workspace_bytes(M,N,K) bytes (only used by the split-K schedule).
+int launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
+                const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace teo

@@ -1,0 +1,481 @@
+// bf16 × bf16 → fp32 GEMM on the 5th-gen tensor cores: C[M,N] = epi(A[M,K] · W[N,K]^T).
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      TMA producer   cp.async.bulk.tensor 2-D tiles of A and W (both K-major, 128-byte
+//                              swizzle) into a STAGES-deep shared-memory ring, mbarrier-signalled
+//   warp 1      MMA issuer     one thread issues tcgen05.mma (UMMA 128×BN×16, cta_group::1),
+//                              accumulating in TMEM; tcgen05.commit releases ring slots
+//   warp 2      TMEM allocator (2 accumulator stages × BN fp32 columns)
+//   warps 4-7   epilogue       tcgen05.ld 32 lanes × 32 columns → bias / activation / residual →
+//                              bf16 (or fp32) stores; overlaps the next tile's MMAs
+//
+// Schedules:
+//   normal      A = activations [M,K], W = weights [N,K]; tiles 128 × 256
+//   swap-AB     small M (decode: M = batch ≤ 128): the weight matrix takes the UMMA M dimension
+//               (128 rows of W per tile), the activations the N dimension (BN = 32/64/128), the
+//               epilogue stores transposed.  Weight streaming is HBM-bound, so tiles are also
+//               split along K to put ≥ 2 work units on every SM; fp32 partials go to the
+//               workspace and a small kernel reduces them in a fixed order (deterministic).
+//
+// Algorithmic work: 2·M·N·K flop; bytes 2·(M·K + N·K + M·N).
+#include <cuda.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace teo {
+
+constexpr int BM = 128;         // UMMA M
+constexpr int BK = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int GEMM_THREADS = 256;
+constexpr int GROUP_M = 16;     // rasterisation group (tiles along M sharing W tiles in L2)
+
+struct GemmArgs {
+    int M, N, K;                // GEMM-space sizes (swap-AB: M = weight rows, N = batch rows)
+    void* C;
+    long long ldc;
+    const bf16* bias;
+    const bf16* residual;
+    long long ldr;
+    int act;
+    int out_fp32;
+    int transposed;             // store C[n*ldc + m], bias indexed by m (swap-AB)
+    int splits;                 // split-K factor; > 1 → fp32 partials, no bias/act/residual here
+    long long split_stride;     // elements between partials
+    int kb_per_split;           // K blocks per split
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == TEO_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+    if (act == TEO_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+__device__ __forceinline__ void unit_to_tile(int unit, const GemmArgs& g, int num_m, int num_n, int& m_blk, int& n_blk,
+                                             int& split) {
+    split = unit % g.splits;
+    const int tile = unit / g.splits;
+    const int group_sz = GROUP_M * num_n;
+    const int grp = tile / group_sz;
+    const int first_m = grp * GROUP_M;
+    const int gm = min(GROUP_M, num_m - first_m);
+    const int in_grp = tile - grp * group_sz;
+    m_blk = first_m + in_grp % gm;
+    n_blk = in_grp / gm;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (g.M + BM - 1) / BM;
+    const int num_n = (g.N + BN - 1) / BN;
+    const int num_units = num_m * num_n * g.splits;
+    const int total_kb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                int m_blk, n_blk, split;
+                unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
+                    tma_load_2d(smem_b + s * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[s], kb * BK, n_blk * BN);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                int m_blk, n_blk, split;
+                unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
+                    const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the
+                        // (address >> 4) field of the descriptor
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);          // frees the ring slot when the MMAs retire
+                    if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                if (kb1 <= kb0) umma_commit(&tfull_bar[as]);   // degenerate (never scheduled)
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        int as = 0;
+        uint32_t aph = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            int m_blk, n_blk, split;
+            unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const int m = m_blk * BM + q * 32 + lane;
+            const bool m_ok = m < g.M;
+            const bool partial = g.splits > 1;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n0 = n_blk * BN + c0;
+                if (n0 >= g.N) break;            // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0, v);
+                tmem_ld_wait();
+                if (g.transposed) {
+                    // C[n, m]: lanes hold consecutive m → coalesced along m for each n
+                    if (partial) {
+                        float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (m_ok && n0 + j < g.N) P[static_cast<long long>(n0 + j) * g.ldc + m] = __uint_as_float(v[j]);
+                    } else {
+                        const float bm = (g.bias && m_ok) ? __bfloat162float(g.bias[m]) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (m_ok && n0 + j < g.N) {
+                                float x = apply_act(__uint_as_float(v[j]) + bm, g.act);
+                                if (g.residual) x += __bfloat162float(g.residual[static_cast<long long>(n0 + j) * g.ldr + m]);
+                                const long long o = static_cast<long long>(n0 + j) * g.ldc + m;
+                                if (g.out_fp32) reinterpret_cast<float*>(g.C)[o] = x;
+                                else reinterpret_cast<bf16*>(g.C)[o] = __float2bfloat16_rn(x);
+                            }
+                        }
+                    }
+                } else if (m_ok) {
+                    // row m, 32 consecutive columns n0..n0+31 (N % 8 == 0 → 8-column groups are all-in or all-out)
+                    if (partial) {
+                        float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride +
+                                   static_cast<long long>(m) * g.ldc + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (n0 + j < g.N)
+                                *reinterpret_cast<float4*>(P + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j0 = 0; j0 < 32; j0 += 8) {
+                            if (n0 + j0 >= g.N) break;
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j0 + j]);
+                            if (g.bias) {
+                                const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n0 + j0);
+                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+                            }
+                            if (g.act != TEO_ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
+                            }
+                            if (g.residual) {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(g.residual + static_cast<long long>(m) * g.ldr + n0 + j0);
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
+                            }
+                            if (g.out_fp32) {
+                                float* o = reinterpret_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
+                                *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+                                *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                            } else {
+                                bf16* o = reinterpret_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
+                                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                                                                          pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// out[i] = bf16/f32( Σ_s partial[s][i] + bias[i % n] ) ... (+act) (+residual) — fixed summation order.
+__global__ void splitk_reduce_kernel(const float* __restrict__ partials, long long split_stride, int splits, void* out,
+                                     long long ldo, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
+                                     long long ldr, int act, int out_fp32, int rows, int cols) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(rows) * cols) return;
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partials[s * split_stride + i];
+    if (bias) acc += __bfloat162float(bias[c]);
+    acc = apply_act(acc, act);
+    if (residual) acc += __bfloat162float(residual[r * ldr + c]);
+    if (out_fp32) reinterpret_cast<float*>(out)[r * ldo + c] = acc;
+    else reinterpret_cast<bf16*>(out)[r * ldo + c] = __float2bfloat16_rn(acc);
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  const CUtensorMap** out) {
+    TmapKey key{ptr, rows, cols, ld, box_rows};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+        *out = &it->second;
+        return TEO_OK;
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return TEO_ERR_CUDA;
+    }
+    TEO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand %p not 16-byte aligned", ptr);
+    TEO_CHECK_ARG((ld * 2) % 16 == 0, "TMA operand leading dimension %llu not a multiple of 8 elements",
+                  (unsigned long long)ld);
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu box %u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return TEO_ERR_CUDA;
+    }
+    if (h->tmaps.size() > 4096) h->tmaps.clear();   // bounded cache
+    auto ins = h->tmaps.emplace(key, m);
+    *out = &ins.first->second;
+    return TEO_OK;
+}
+
+struct GemmPlan {
+    bool swap;
+    int bn;
+    int splits;
+    int kb_per_split;
+};
+
+static GemmPlan plan_gemm(int M, int N, int K, int num_sms) {
+    GemmPlan p;
+    const int total_kb = (K + BK - 1) / BK;
+    p.swap = (M <= 128) && (N >= 256);
+    p.splits = 1;
+    p.kb_per_split = total_kb;
+    if (p.swap) {
+        p.bn = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
+        const int tiles = (N + BM - 1) / BM;
+        int want = (2 * num_sms + tiles - 1) / tiles;           // ≥ 2 work units per SM
+        want = std::max(1, std::min(want, std::max(1, total_kb / 4)));
+        want = std::min(want, 16);
+        p.kb_per_split = (total_kb + want - 1) / want;
+        p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    } else {
+        p.bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+    }
+    return p;
+}
+
+}  // namespace teo
+
+using namespace teo;
+
+extern "C" size_t teo_gemm_workspace_bytes(int M, int N, int K) {
+    GemmPlan p = plan_gemm(M, N, K, 148);
+    // independent of the SM count actually present: plan with the max split factor
+    if (!p.swap) return 0;
+    return static_cast<size_t>(16) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float);
+}
+
+template <int BN>
+static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& g, int units,
+                      cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TEO_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = std::min(units, h->num_sms);
+    gemm_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, g);
+    TEO_LAUNCH_CHECK("gemm_tn_kernel");
+    h->launches++;
+    return TEO_OK;
+}
+
+int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N,
+                     int K, const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    TEO_CHECK_ARG(h != nullptr, "null handle");
+    TEO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive size M=%d N=%d K=%d", M, N, K);
+    TEO_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
+    TEO_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "gemm: leading dimension too small");
+    TEO_CHECK_ARG(ldc % (ep.out_fp32 ? 4 : 8) == 0, "gemm: ldc (%d) breaks 16-byte row alignment", ldc);
+    TEO_CHECK_ARG(ep.residual == nullptr || ep.ldr % 8 == 0, "gemm: ldr (%d) must be a multiple of 8", ep.ldr);
+    TEO_CHECK_ARG((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: C not 16-byte aligned");
+    TEO_CHECK_ARG(ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0, "gemm: bias not 16-byte aligned");
+    TEO_CHECK_ARG(ep.residual == nullptr || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0,
+                  "gemm: residual not 16-byte aligned");
+    const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
+    GemmArgs g{};
+    g.act = ep.act;
+    g.out_fp32 = ep.out_fp32;
+    g.bias = ep.bias;
+    g.residual = ep.residual;
+    g.ldr = ep.ldr;
+    g.C = C;
+    g.ldc = ldc;
+    g.K = K;
+    g.splits = p.splits;
+    g.kb_per_split = p.kb_per_split;
+    const CUtensorMap *ta, *tb;
+    if (p.swap) {
+        g.M = N;   // weight rows on the UMMA M dimension
+        g.N = M;
+        g.transposed = 1;
+        TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
+        TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
+        if (p.splits > 1) {
+            const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
+            if (workspace == nullptr || workspace_bytes < need) {
+                set_error("gemm: split-K needs %zu workspace bytes, got %zu", need, workspace_bytes);
+                return TEO_ERR_WORKSPACE;
+            }
+            g.C = workspace;
+            g.ldc = N;                       // partial layout [split][M_act][N_out]
+            g.split_stride = static_cast<long long>(M) * N;
+        }
+    } else {
+        g.M = M;
+        g.N = N;
+        g.transposed = 0;
+        TEO_TRY(get_tmap_bf16(h, A, M, K, lda, BM, &ta));
+        TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
+    }
+    const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
+    int rc;
+    switch (p.bn) {
+        case 32: rc = launch_cfg<32>(h, ta, tb, g, units, stream); break;
+        case 64: rc = launch_cfg<64>(h, ta, tb, g, units, stream); break;
+        case 128: rc = launch_cfg<128>(h, ta, tb, g, units, stream); break;
+        default: rc = launch_cfg<256>(h, ta, tb, g, units, stream); break;
+    }
+    TEO_TRY(rc);
+    if (p.swap && p.splits > 1) {
+        const long long total = static_cast<long long>(M) * N;
+        const int threads = 256;
+        const int blocks = static_cast<int>((total + threads - 1) / threads);
+        splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(workspace), total, p.splits, C,
+                                                             ldc, ep.bias, ep.residual, ep.ldr, ep.act, ep.out_fp32, M, N);
+        TEO_LAUNCH_CHECK("splitk_reduce_kernel");
+        h->launches++;
+    }
+    return TEO_OK;
+}
+
+extern "C" int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M,
+                             int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    TEO_CHECK_ARG(A && W && C, "gemm: null operand");
+    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_GELU, "gemm: unknown activation %d", act);
+    GemmEpilogue ep;
+    ep.bias = static_cast<const bf16*>(bias);
+    ep.residual = static_cast<const bf16*>(residual);
+    ep.ldr = ldr;
+    ep.act = act;
+    ep.out_fp32 = out_fp32;
+    return launch_gemm(h, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, ep,
+                       workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}

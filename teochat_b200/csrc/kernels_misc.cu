@@ -1,0 +1,461 @@
+// HBM-bound helper kernels of the hot path: synthetic init, patchify (normalise + im2col),
+// embeddings + LayerNorm, RMSNorm, SwiGLU, RoPE + KV-page scatter, splice gather, greedy argmax.
+// All are one-pass, 16-byte-vectorised where the layout allows, fp32 math on bf16 storage.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace teo {
+
+// ------------------------------------------------------------------------------ synthetic init
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_normal_at(uint64_t seed, size_t i, float scale, float mean) {
+    const uint64_t x = splitmix64(seed + (static_cast<uint64_t>(i) + 1ULL) * 0x9E3779B97F4A7C15ULL);
+    const int s = static_cast<int>(x & 0xFFFF) + static_cast<int>((x >> 16) & 0xFFFF) +
+                  static_cast<int>((x >> 32) & 0xFFFF) + static_cast<int>((x >> 48) & 0xFFFF);
+    return __fadd_rn(mean, __fmul_rn(static_cast<float>(s - 131070), scale));   // no FMA contraction
+}
+template <typename T>
+__global__ void init_normal_hash_kernel(T* out, size_t n, uint64_t seed, float scale, float mean) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = hash_normal_at(seed, i, scale, mean);
+        if constexpr (sizeof(T) == 2) out[i] = __float2bfloat16_rn(v);
+        else out[i] = v;
+    }
+}
+__global__ void init_u8_hash_kernel(uint8_t* out, size_t n, uint64_t seed) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = static_cast<uint8_t>(splitmix64(seed + (static_cast<uint64_t>(i) + 1ULL) * 0x9E3779B97F4A7C15ULL) >> 56);
+}
+
+// ------------------------------------------------------------------------------ patchify
+// One block per (frame, patch row): stage the P image rows in shared memory with coalesced loads,
+// then emit g patches × kpad bf16 columns, column index (c*P + ky)*P + kx.
+template <bool U8>
+__global__ void patchify_kernel(const void* __restrict__ in, bf16* __restrict__ patches, int image, int patch, int kpad) {
+    extern __shared__ float tile[];   // [3][P][image] normalised values
+    const int g = image / patch;
+    const int frame = blockIdx.x / g, py = blockIdx.x % g;
+    const int row_elems = image * 3;
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    if constexpr (U8) {
+        const uint8_t* src = static_cast<const uint8_t*>(in) + (static_cast<size_t>(frame) * image + static_cast<size_t>(py) * patch) * row_elems;
+        for (int i = threadIdx.x; i < patch * row_elems; i += blockDim.x) {
+            const int ky = i / row_elems, r = i % row_elems, x = r / 3, c = r % 3;
+            const float v = __fdiv_rn(static_cast<float>(src[i]), 255.0f);      // ToTensor
+            tile[(c * patch + ky) * image + x] = __fdiv_rn(v - mean[c], stdv[c]);   // Normalize
+        }
+    } else {
+        const float* src = static_cast<const float*>(in) + static_cast<size_t>(frame) * 3 * image * image;
+        for (int i = threadIdx.x; i < 3 * patch * image; i += blockDim.x) {
+            const int c = i / (patch * image), r = i % (patch * image), ky = r / image, x = r % image;
+            tile[(c * patch + ky) * image + x] = src[(static_cast<size_t>(c) * image + py * patch + ky) * image + x];
+        }
+    }
+    __syncthreads();
+    const int pdim = 3 * patch * patch;
+    bf16* dst = patches + (static_cast<size_t>(frame) * g * g + static_cast<size_t>(py) * g) * kpad;
+    for (int i = threadIdx.x; i < g * kpad; i += blockDim.x) {
+        const int px = i / kpad, col = i % kpad;
+        float v = 0.f;
+        if (col < pdim) {
+            const int c = col / (patch * patch), r = col % (patch * patch), ky = r / patch, kx = r % patch;
+            v = tile[(c * patch + ky) * image + px * patch + kx];
+        }
+        dst[static_cast<size_t>(px) * kpad + col] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------ row-wise norms
+// TPR threads cooperate on one row; each holds up to MAXV 8-element vectors in registers.
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* smem_red) {
+    v = warp_sum(v);
+    if constexpr (TPR > 32) {
+        const int w = (threadIdx.x % TPR) >> 5, row_in_block = threadIdx.x / TPR;
+        constexpr int WPR = TPR / 32;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) smem_red[row_in_block * WPR + w] = v;
+        __syncthreads();
+        v = 0.f;
+#pragma unroll
+        for (int i = 0; i < WPR; ++i) v += smem_red[row_in_block * WPR + i];
+    }
+    return v;
+}
+
+constexpr int NORM_MAXV = 8;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&x)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { x[2 * j] = bf16_lo(w[j]); x[2 * j + 1] = bf16_hi(w[j]); }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&x)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                              pack_bf16x2(x[6], x[7]));
+}
+
+// MODE 0: LayerNorm(x)            (x row = in[row])
+// MODE 1: ViT embeddings: x row = (tok==0 ? cls : patch_out[frame*np + tok-1]) + pos[tok], then LayerNorm
+// MODE 2: RMSNorm(x)
+template <int TPR, int MODE>
+__global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                            bf16* __restrict__ out, int rows, int d, float eps, const bf16* __restrict__ cls,
+                            const bf16* __restrict__ pos, int n_patches) {
+    __shared__ float red[32];
+    constexpr int RPB = 128 / TPR;   // rows per 128-thread block
+    const int row = blockIdx.x * RPB + threadIdx.x / TPR;
+    const int t = threadIdx.x % TPR;
+    const bool active = row < rows;
+    float x[NORM_MAXV][8];
+    float sum = 0.f;
+    const bf16* src = in;
+    const bf16* posrow = nullptr;
+    if (active) {
+        if constexpr (MODE == 1) {
+            const int tok = row % (n_patches + 1), frame = row / (n_patches + 1);
+            src = tok == 0 ? cls : in + (static_cast<size_t>(frame) * n_patches + tok - 1) * d;
+            posrow = pos + static_cast<size_t>(tok) * d;
+        } else {
+            src = in + static_cast<size_t>(row) * d;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NORM_MAXV; ++v) {
+        const int c = (v * TPR + t) * 8;
+        if (active && c < d) {
+            load8(src + c, x[v]);
+            if constexpr (MODE == 1) {
+                float p[8];
+                load8(posrow + c, p);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[v][j] += p[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += (MODE == 2) ? x[v][j] * x[v][j] : x[v][j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[v][j] = 0.f;
+        }
+    }
+    sum = row_sum<TPR>(sum, red);
+    float mean = 0.f, rstd;
+    if constexpr (MODE == 2) {
+        rstd = 1.0f / sqrtf(sum / static_cast<float>(d) + eps);
+    } else {
+        mean = sum / static_cast<float>(d);
+        float sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < NORM_MAXV; ++v) {
+            const int c = (v * TPR + t) * 8;
+            if (active && c < d) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float dlt = x[v][j] - mean; sq += dlt * dlt; }
+            }
+        }
+        sq = row_sum<TPR>(sq, red);
+        rstd = 1.0f / sqrtf(sq / static_cast<float>(d) + eps);
+    }
+    if (!active) return;
+    bf16* dst = out + static_cast<size_t>(row) * d;
+#pragma unroll
+    for (int v = 0; v < NORM_MAXV; ++v) {
+        const int c = (v * TPR + t) * 8;
+        if (c < d) {
+            float wv[8], y[8];
+            load8(w + c, wv);
+            if constexpr (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (x[v][j] * rstd) * wv[j];
+            } else {
+                float bv[8];
+                load8(b + c, bv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (x[v][j] - mean) * rstd * wv[j] + bv[j];
+            }
+            store8(dst + c, y);
+        }
+    }
+}
+
+template <int MODE>
+static int launch_norm(const bf16* in, const bf16* w, const bf16* b, bf16* out, int rows, int d, float eps, const bf16* cls,
+                       const bf16* pos, int n_patches, cudaStream_t stream) {
+    TEO_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0, "norm: rows=%d d=%d (d must be a positive multiple of 8)", rows, d);
+    TEO_CHECK_ARG(d <= 128 * 8 * NORM_MAXV, "norm: d=%d exceeds %d", d, 128 * 8 * NORM_MAXV);
+    if (d <= 32 * 8 * 4) {
+        norm_kernel<32, MODE><<<(rows + 3) / 4, 128, 0, stream>>>(in, w, b, out, rows, d, eps, cls, pos, n_patches);
+    } else {
+        norm_kernel<128, MODE><<<rows, 128, 0, stream>>>(in, w, b, out, rows, d, eps, cls, pos, n_patches);
+    }
+    TEO_LAUNCH_CHECK("norm_kernel");
+    return TEO_OK;
+}
+
+// ------------------------------------------------------------------------------ small copies / elementwise
+__global__ void drop_cls_kernel(const uint4* __restrict__ hidden, uint4* __restrict__ feats, int n_patches, int d8, size_t total) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t row = i / d8, c = i % d8;
+        const size_t frame = row / n_patches, tok = row % n_patches;
+        feats[i] = hidden[(frame * (n_patches + 1) + tok + 1) * d8 + c];
+    }
+}
+
+__global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict__ out, int rows, int inter) {
+    const int i8 = inter / 8;
+    const size_t total = static_cast<size_t>(rows) * i8;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / i8, c = (i % i8) * 8;
+        float g[8], u[8], y[8];
+        load8(gate_up + r * 2 * inter + c, g);
+        load8(gate_up + r * 2 * inter + inter + c, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (g[j] / (1.0f + expf(-g[j]))) * u[j];
+        store8(out + r * inter + c, y);
+    }
+}
+
+__global__ void splice_embed_kernel(const bf16* __restrict__ embed, const bf16* __restrict__ feats, const int* __restrict__ src,
+                                    bf16* __restrict__ out, int tokens, int d8) {
+    const int row = blockIdx.x;
+    if (row >= tokens) return;
+    const int s = src[row];
+    const uint4* from = reinterpret_cast<const uint4*>(s >= 0 ? embed + static_cast<size_t>(s) * d8 * 8
+                                                              : feats + static_cast<size_t>(-(s + 1)) * d8 * 8);
+    uint4* to = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d8 * 8);
+    for (int c = threadIdx.x; c < d8; c += blockDim.x) to[c] = from[c];
+}
+
+// ------------------------------------------------------------------------------ RoPE + KV scatter
+// One warp per (token, head).  rotate-half: out[i] = x[i]cos_i - x[i+h/2]sin_i; out[i+h/2] = x[i+h/2]cos_i + x[i]sin_i.
+// cos/sin tables f32 [max_pos, hd/2] are built on the host exactly like HF's cached tables.
+__global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restrict__ positions, const int* __restrict__ seq_ids,
+                                     bf16* __restrict__ kv_pages, const int* __restrict__ block_table, int max_pages, int tokens,
+                                     int n_heads, int head_dim, int page_size, const float* __restrict__ rope_cos,
+                                     const float* __restrict__ rope_sin) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= tokens * n_heads) return;
+    const int tok = gw / n_heads, head = gw % n_heads;
+    const int hidden = n_heads * head_dim, half = head_dim / 2;
+    const int pos = positions[tok];
+    const int seq = seq_ids ? seq_ids[tok] : tok;
+    const int page = block_table[static_cast<size_t>(seq) * max_pages + pos / page_size];
+    const int slot = pos % page_size;
+    bf16* q = qkv + static_cast<size_t>(tok) * 3 * hidden + head * head_dim;
+    bf16* k = q + hidden;
+    const bf16* v = k + hidden;
+    // page layout [page][2][head][slot][dim]
+    bf16* kdst = kv_pages + (((static_cast<size_t>(page) * 2 + 0) * n_heads + head) * page_size + slot) * head_dim;
+    bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim;
+    const float* cs = rope_cos + static_cast<size_t>(pos) * half;
+    const float* sn = rope_sin + static_cast<size_t>(pos) * half;
+    for (int i = lane * 2; i < half; i += 64) {
+        const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
+        {
+            const uint32_t lo = *reinterpret_cast<const uint32_t*>(q + i), hi = *reinterpret_cast<const uint32_t*>(q + i + half);
+            const float a0 = bf16_lo(lo), a1 = bf16_hi(lo), b0 = bf16_lo(hi), b1 = bf16_hi(hi);
+            *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+            *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+        }
+        {
+            const uint32_t lo = *reinterpret_cast<const uint32_t*>(k + i), hi = *reinterpret_cast<const uint32_t*>(k + i + half);
+            const float a0 = bf16_lo(lo), a1 = bf16_hi(lo), b0 = bf16_lo(hi), b1 = bf16_hi(hi);
+            const uint32_t o_lo = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+            const uint32_t o_hi = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+            *reinterpret_cast<uint32_t*>(k + i) = o_lo;
+            *reinterpret_cast<uint32_t*>(k + i + half) = o_hi;
+            *reinterpret_cast<uint32_t*>(kdst + i) = o_lo;
+            *reinterpret_cast<uint32_t*>(kdst + i + half) = o_hi;
+        }
+    }
+    for (int i = lane * 2; i < head_dim; i += 64)
+        *reinterpret_cast<uint32_t*>(vdst + i) = *reinterpret_cast<const uint32_t*>(v + i);
+}
+
+// ------------------------------------------------------------------------------ greedy argmax + stop rule
+// One block per sequence.  Ties → lowest index (torch.argmax semantics).  When step_ptr != NULL
+// the column is read from device memory (graph replay) and block 0 bumps it afterwards.
+__global__ void argmax_step_kernel(const float* __restrict__ logits, int vocab, uint8_t* finished, int* tokens, int max_new,
+                                   int step_host, int* step_ptr, int* next_ids, int* seq_lens, int eos_id) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    const int seq = blockIdx.x;
+    const float* row = logits + static_cast<size_t>(seq) * vocab;
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+        const int step = step_ptr ? *step_ptr : step_host;
+        const bool was_done = finished[seq] != 0;
+        const int tok = was_done ? eos_id : idx;
+        if (step < max_new) tokens[static_cast<size_t>(seq) * max_new + step] = was_done ? -1 : tok;
+        if (!was_done && tok == eos_id) finished[seq] = 1;
+        next_ids[seq] = tok;
+        if (seq_lens) seq_lens[seq] += 1;
+    }
+}
+__global__ void bump_step_kernel(int* step_ptr) { *step_ptr += 1; }
+
+}  // namespace teo
+
+using namespace teo;
+
+static inline int grid_for(size_t n, int threads) {
+    size_t b = (n + threads - 1) / threads;
+    return static_cast<int>(b > 148 * 32 ? 148 * 32 : (b == 0 ? 1 : b));
+}
+
+extern "C" int teo_init_normal_hash_bf16(void* out, size_t n, uint64_t seed, float scale, float mean, void* stream) {
+    TEO_CHECK_ARG(out || n == 0, "init: null output");
+    if (n == 0) return TEO_OK;
+    init_normal_hash_kernel<bf16><<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16*>(out), n, seed, scale, mean);
+    TEO_LAUNCH_CHECK("init_normal_hash_kernel");
+    return TEO_OK;
+}
+extern "C" int teo_init_normal_hash_f32(void* out, size_t n, uint64_t seed, float scale, float mean, void* stream) {
+    TEO_CHECK_ARG(out || n == 0, "init: null output");
+    if (n == 0) return TEO_OK;
+    init_normal_hash_kernel<float><<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(out), n, seed, scale, mean);
+    TEO_LAUNCH_CHECK("init_normal_hash_kernel");
+    return TEO_OK;
+}
+extern "C" int teo_init_u8_hash(void* out, size_t n, uint64_t seed, void* stream) {
+    TEO_CHECK_ARG(out || n == 0, "init: null output");
+    if (n == 0) return TEO_OK;
+    init_u8_hash_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint8_t*>(out), n, seed);
+    TEO_LAUNCH_CHECK("init_u8_hash_kernel");
+    return TEO_OK;
+}
+
+static int patchify_common(bool u8, const void* in, void* patches, int n_frames, int image, int patch, int kpad, void* stream) {
+    TEO_CHECK_ARG(in && patches, "patchify: null pointer");
+    TEO_CHECK_ARG(n_frames > 0 && image > 0 && patch > 0 && image % patch == 0, "patchify: bad geometry image=%d patch=%d", image, patch);
+    TEO_CHECK_ARG(kpad >= 3 * patch * patch && kpad % 8 == 0, "patchify: kpad=%d must be >= %d and a multiple of 8", kpad, 3 * patch * patch);
+    const int g = image / patch;
+    const size_t smem = static_cast<size_t>(3) * patch * image * sizeof(float);
+    TEO_CHECK_ARG(smem <= 48 * 1024, "patchify: image row tile (%zu B) exceeds 48 KiB", smem);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (u8) patchify_kernel<true><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+    else patchify_kernel<false><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+    TEO_LAUNCH_CHECK("patchify_kernel");
+    return TEO_OK;
+}
+extern "C" int teo_patchify_u8_nhwc(const void* frames_u8, void* patches, int n_frames, int image, int patch, int kpad, void* stream) {
+    return patchify_common(true, frames_u8, patches, n_frames, image, patch, kpad, stream);
+}
+extern "C" int teo_patchify_f32_nchw(const void* pixel_values, void* patches, int n_frames, int image, int patch, int kpad, void* stream) {
+    return patchify_common(false, pixel_values, patches, n_frames, image, patch, kpad, stream);
+}
+
+extern "C" int teo_vit_assemble_preln(const void* patch_out, const void* cls, const void* pos, const void* ln_w, const void* ln_b,
+                                      void* hidden, int n_frames, int n_patches, int d, float eps, void* stream) {
+    TEO_CHECK_ARG(patch_out && cls && pos && ln_w && ln_b && hidden, "vit_assemble_preln: null pointer");
+    TEO_CHECK_ARG(n_frames > 0 && n_patches > 0, "vit_assemble_preln: bad sizes");
+    return launch_norm<1>(static_cast<const bf16*>(patch_out), static_cast<const bf16*>(ln_w), static_cast<const bf16*>(ln_b),
+                          static_cast<bf16*>(hidden), n_frames * (n_patches + 1), d, eps, static_cast<const bf16*>(cls),
+                          static_cast<const bf16*>(pos), n_patches, static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int d, float eps, void* stream) {
+    TEO_CHECK_ARG(x && w && b && y, "layernorm: null pointer");
+    return launch_norm<0>(static_cast<const bf16*>(x), static_cast<const bf16*>(w), static_cast<const bf16*>(b), static_cast<bf16*>(y),
+                          rows, d, eps, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_rmsnorm(const void* x, const void* w, void* y, int rows, int d, float eps, void* stream) {
+    TEO_CHECK_ARG(x && w && y, "rmsnorm: null pointer");
+    return launch_norm<2>(static_cast<const bf16*>(x), static_cast<const bf16*>(w), nullptr, static_cast<bf16*>(y), rows, d, eps,
+                          nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_vit_drop_cls(const void* hidden, void* feats, int n_frames, int n_patches, int d, void* stream) {
+    TEO_CHECK_ARG(hidden && feats, "vit_drop_cls: null pointer");
+    TEO_CHECK_ARG(n_frames > 0 && n_patches > 0 && d > 0 && d % 8 == 0, "vit_drop_cls: bad sizes");
+    const size_t total = static_cast<size_t>(n_frames) * n_patches * (d / 8);
+    drop_cls_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(hidden), static_cast<uint4*>(feats), n_patches, d / 8, total);
+    TEO_LAUNCH_CHECK("drop_cls_kernel");
+    return TEO_OK;
+}
+extern "C" int teo_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream) {
+    TEO_CHECK_ARG(gate_up && out, "swiglu: null pointer");
+    TEO_CHECK_ARG(rows > 0 && inter > 0 && inter % 8 == 0, "swiglu: rows=%d inter=%d", rows, inter);
+    const size_t total = static_cast<size_t>(rows) * (inter / 8);
+    swiglu_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(gate_up),
+                                                                                     static_cast<bf16*>(out), rows, inter);
+    TEO_LAUNCH_CHECK("swiglu_kernel");
+    return TEO_OK;
+}
+extern "C" int teo_splice_embed(const void* embed_tokens, const void* image_feats, const void* src, void* out, int tokens, int d,
+                                void* stream) {
+    TEO_CHECK_ARG(embed_tokens && src && out, "splice_embed: null pointer");
+    TEO_CHECK_ARG(tokens > 0 && d > 0 && d % 8 == 0, "splice_embed: tokens=%d d=%d", tokens, d);
+    splice_embed_kernel<<<tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(embed_tokens),
+                                                                             static_cast<const bf16*>(image_feats),
+                                                                             static_cast<const int*>(src), static_cast<bf16*>(out), tokens, d / 8);
+    TEO_LAUNCH_CHECK("splice_embed_kernel");
+    return TEO_OK;
+}
+
+namespace teo {
+int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, void* kv_pages, const int* block_table, int max_pages,
+                         int tokens, int n_heads, int head_dim, int page_size, const float* rope_cos, const float* rope_sin,
+                         cudaStream_t stream) {
+    TEO_CHECK_ARG(qkv && positions && kv_pages && block_table && rope_cos && rope_sin, "rope_kv_write: null pointer");
+    TEO_CHECK_ARG(tokens > 0 && n_heads > 0 && head_dim > 0 && head_dim % 4 == 0 && page_size > 0, "rope_kv_write: bad sizes");
+    const long long warps = static_cast<long long>(tokens) * n_heads;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    rope_kv_write_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(static_cast<bf16*>(qkv), positions, seq_ids,
+                                                                               static_cast<bf16*>(kv_pages), block_table, max_pages, tokens,
+                                                                               n_heads, head_dim, page_size, rope_cos, rope_sin);
+    TEO_LAUNCH_CHECK("rope_kv_write_kernel");
+    return TEO_OK;
+}
+int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
+                       int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream) {
+    TEO_CHECK_ARG(logits && finished && tokens && next_ids, "argmax_step: null pointer");
+    TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0, "argmax_step: bad sizes");
+    argmax_step_kernel<<<n_seqs, 256, 0, stream>>>(logits, vocab, finished, tokens, max_new, step_host, step_ptr, next_ids, seq_lens, eos_id);
+    TEO_LAUNCH_CHECK("argmax_step_kernel");
+    if (step_ptr) {
+        bump_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+        TEO_LAUNCH_CHECK("bump_step_kernel");
+    }
+    return TEO_OK;
+}
+}  // namespace teo
+
+extern "C" int teo_rope_kv_write(void* qkv, const void* positions, const void* seq_ids, void* kv_pages, const void* block_table,
+                                 int max_pages, int tokens, int n_heads, int head_dim, int page_size, const void* rope_cos,
+                                 const void* rope_sin, void* stream) {
+    return launch_rope_kv_write(qkv, static_cast<const int*>(positions), static_cast<const int*>(seq_ids), kv_pages,
+                                static_cast<const int*>(block_table), max_pages, tokens, n_heads, head_dim, page_size,
+                                static_cast<const float*>(rope_cos), static_cast<const float*>(rope_sin), static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_argmax_step(const void* logits, int vocab, void* finished, void* tokens, int max_new, int step, void* next_ids,
+                               int n_seqs, int eos_id, void* stream) {
+    return launch_argmax_step(static_cast<const float*>(logits), vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new,
+                              step, nullptr, static_cast<int*>(next_ids), nullptr, n_seqs, eos_id, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,385 @@
+// C-ABI lifecycle + whole-model entry points (ViT encode, projector, LLaMA prefill, decode step):
+// fixed launch sequences over the kernels in gemm.cu / attention.cu / kernels_misc.cu.  No
+// allocation, no host synchronisation — every call only enqueues on the caller's stream, so the
+// decode step can be captured in a CUDA graph.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "common.h"
+
+namespace teo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int launch_flash_attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
+                           const int* cu_seqlens, int n_seqs, int max_seqlen, int n_heads, int head_dim, float scale,
+                           int causal, cudaStream_t stream);
+int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* kv_pages, const int* block_table, int max_pages,
+                            const int* seq_lens, int len_bias, bf16* out, int n_seqs, int n_heads, int head_dim, int page_size,
+                            int max_seq_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, void* kv_pages, const int* block_table, int max_pages,
+                         int tokens, int n_heads, int head_dim, int page_size, const float* rope_cos, const float* rope_sin,
+                         cudaStream_t stream);
+int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
+                       int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
+
+__global__ void fill_cu_seqlens_kernel(int* cu, int n, int len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) cu[i] = i * len;
+}
+
+// bump allocator over the caller's workspace (256-byte aligned slices)
+struct Arena {
+    uint8_t* base;
+    size_t size, off = 0;
+    bool ok = true;
+    Arena(void* p, size_t n) : base(static_cast<uint8_t*>(p)), size(n) {}
+    template <typename T>
+    T* take(size_t count) {
+        const size_t bytes = (count * sizeof(T) + 255) & ~static_cast<size_t>(255);
+        if (base == nullptr || off + bytes > size) {
+            ok = false;
+            off += bytes;
+            return nullptr;
+        }
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+static inline size_t al256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace teo
+
+using namespace teo;
+
+// ------------------------------------------------------------------------------ lifecycle
+extern "C" const char* teo_last_error(void) { return g_err; }
+extern "C" int teo_abi_version(void) { return 1; }
+
+extern "C" int teo_create(int device_id, teo_handle** out) {
+    TEO_CHECK_ARG(out != nullptr, "teo_create: null out");
+    *out = nullptr;
+    int count = 0;
+    TEO_CUDA(cudaGetDeviceCount(&count));
+    TEO_CHECK_ARG(device_id >= 0 && device_id < count, "teo_create: device %d not in [0,%d)", device_id, count);
+    TEO_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    TEO_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) {
+        set_error("teo_create: device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
+        return TEO_ERR_UNSUPPORTED;
+    }
+    teo_handle* h = new (std::nothrow) teo_handle();
+    TEO_CHECK_ARG(h != nullptr, "teo_create: out of host memory");
+    h->device = device_id;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return TEO_OK;
+}
+extern "C" int teo_destroy(teo_handle* h) {
+    delete h;
+    return TEO_OK;
+}
+extern "C" unsigned long long teo_launch_count(const teo_handle* h) { return h ? h->launches : 0ULL; }
+
+// ------------------------------------------------------------------------------ ViT
+static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patches, bf16** patch_out, bf16** hidden, bf16** ln_out,
+                            bf16** qkv, bf16** attn, bf16** mlp, int** cu) {
+    const int g = m->image / m->patch, np = g * g;
+    const size_t rows = static_cast<size_t>(n) * (np + 1);
+    Arena local(nullptr, 0);
+    Arena& A = a ? *a : local;
+    bf16* p;
+    p = A.take<bf16>(static_cast<size_t>(n) * np * m->kpad); if (patches) *patches = p;
+    p = A.take<bf16>(static_cast<size_t>(n) * np * m->hidden); if (patch_out) *patch_out = p;
+    p = A.take<bf16>(rows * m->hidden); if (hidden) *hidden = p;
+    p = A.take<bf16>(rows * m->hidden); if (ln_out) *ln_out = p;
+    p = A.take<bf16>(rows * 3 * m->hidden); if (qkv) *qkv = p;
+    p = A.take<bf16>(rows * m->hidden); if (attn) *attn = p;
+    p = A.take<bf16>(rows * m->inter); if (mlp) *mlp = p;
+    int* c = A.take<int>(n + 1); if (cu) *cu = c;
+    return A.off;
+}
+
+extern "C" size_t teo_vit_workspace_bytes(const teo_vit_model* m, int n_frames) {
+    if (!m || n_frames <= 0) return 0;
+    return vit_ws_layout(m, n_frames, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void* frames_u8, const void* pixel_values, int n_frames,
+                              void* feats, void* workspace, size_t workspace_bytes, void* stream_) {
+    TEO_CHECK_ARG(h && m && feats, "vit_encode: null pointer");
+    TEO_CHECK_ARG((frames_u8 != nullptr) != (pixel_values != nullptr), "vit_encode: pass exactly one of frames_u8 / pixel_values");
+    TEO_CHECK_ARG(n_frames > 0, "vit_encode: n_frames=%d", n_frames);
+    TEO_CHECK_ARG(m->hidden % m->heads == 0 && m->layers_run >= 0 && m->layers != nullptr, "vit_encode: bad model");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int g = m->image / m->patch, np = g * g, d = m->hidden, hd = d / m->heads;
+    const int rows = n_frames * (np + 1);
+    Arena A(workspace, workspace_bytes);
+    bf16 *patches, *patch_out, *hidden, *ln_out, *qkv, *attn, *mlp;
+    int* cu;
+    vit_ws_layout(m, n_frames, &A, &patches, &patch_out, &hidden, &ln_out, &qkv, &attn, &mlp, &cu);
+    if (!A.ok) {
+        set_error("vit_encode: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
+        return TEO_ERR_WORKSPACE;
+    }
+    if (frames_u8) TEO_TRY(teo_patchify_u8_nhwc(frames_u8, patches, n_frames, m->image, m->patch, m->kpad, stream));
+    else TEO_TRY(teo_patchify_f32_nchw(pixel_values, patches, n_frames, m->image, m->patch, m->kpad, stream));
+    GemmEpilogue none;
+    TEO_TRY(launch_gemm(h, patches, m->kpad, static_cast<const bf16*>(m->patch_w), m->kpad, patch_out, d, n_frames * np, d, m->kpad,
+                        none, nullptr, 0, stream));
+    TEO_TRY(teo_vit_assemble_preln(patch_out, m->cls, m->pos, m->pre_ln_w, m->pre_ln_b, hidden, n_frames, np, d, m->eps, stream));
+    fill_cu_seqlens_kernel<<<(n_frames + 256) / 256, 256, 0, stream>>>(cu, n_frames, np + 1);
+    TEO_LAUNCH_CHECK("fill_cu_seqlens_kernel");
+    h->launches += 3;
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    for (int l = 0; l < m->layers_run; ++l) {
+        const teo_vit_layer& L = m->layers[l];
+        TEO_TRY(teo_layernorm(hidden, L.ln1_w, L.ln1_b, ln_out, rows, d, m->eps, stream));
+        GemmEpilogue e1;
+        e1.bias = static_cast<const bf16*>(L.qkv_b);
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, nullptr, 0, stream));
+        TEO_TRY(launch_flash_attention(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, m->heads, hd, scale,
+                                       0, stream));
+        GemmEpilogue e2;
+        e2.bias = static_cast<const bf16*>(L.out_b);
+        e2.residual = hidden;
+        e2.ldr = d;
+        TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, nullptr, 0, stream));
+        TEO_TRY(teo_layernorm(hidden, L.ln2_w, L.ln2_b, ln_out, rows, d, m->eps, stream));
+        GemmEpilogue e3;
+        e3.bias = static_cast<const bf16*>(L.fc1_b);
+        e3.act = m->act;
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.fc1_w), d, mlp, m->inter, rows, m->inter, d, e3, nullptr, 0, stream));
+        GemmEpilogue e4;
+        e4.bias = static_cast<const bf16*>(L.fc2_b);
+        e4.residual = hidden;
+        e4.ldr = d;
+        TEO_TRY(launch_gemm(h, mlp, m->inter, static_cast<const bf16*>(L.fc2_w), m->inter, hidden, d, rows, d, m->inter, e4, nullptr, 0,
+                            stream));
+        h->launches += 3;
+    }
+    TEO_TRY(teo_vit_drop_cls(hidden, feats, n_frames, np, d, stream));
+    h->launches += 1;
+    return TEO_OK;
+}
+
+// ------------------------------------------------------------------------------ projector
+extern "C" size_t teo_projector_workspace_bytes(const teo_projector* p, int rows) {
+    if (!p || rows <= 0) return 0;
+    return al256(static_cast<size_t>(rows) * p->hidden * sizeof(bf16)) + al256(teo_gemm_workspace_bytes(rows, p->hidden, p->hidden));
+}
+
+extern "C" int teo_projector_mlp2x(teo_handle* h, const teo_projector* p, const void* feats, int rows, void* out, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+    TEO_CHECK_ARG(h && p && feats && out, "projector: null pointer");
+    TEO_CHECK_ARG(rows > 0, "projector: rows=%d", rows);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Arena A(workspace, workspace_bytes);
+    bf16* mid = A.take<bf16>(static_cast<size_t>(rows) * p->hidden);
+    const size_t gws = teo_gemm_workspace_bytes(rows, p->hidden, p->hidden);
+    uint8_t* gw = A.take<uint8_t>(gws);
+    if (!A.ok) {
+        set_error("projector: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
+        return TEO_ERR_WORKSPACE;
+    }
+    GemmEpilogue e0;
+    e0.bias = static_cast<const bf16*>(p->b0);
+    e0.act = TEO_ACT_GELU;
+    TEO_TRY(launch_gemm(h, static_cast<const bf16*>(feats), p->in_dim, static_cast<const bf16*>(p->w0), p->in_dim, mid, p->hidden, rows,
+                        p->hidden, p->in_dim, e0, gw, gws, stream));
+    GemmEpilogue e1;
+    e1.bias = static_cast<const bf16*>(p->b2);
+    TEO_TRY(launch_gemm(h, mid, p->hidden, static_cast<const bf16*>(p->w2), p->hidden, out, p->hidden, rows, p->hidden, p->hidden, e1, gw,
+                        gws, stream));
+    return TEO_OK;
+}
+
+// ------------------------------------------------------------------------------ LLaMA prefill
+struct PrefillWs {
+    bf16 *norm_out, *qkv, *attn, *gate_up, *act, *last_x, *last_norm;
+    uint8_t* gemm_ws;
+    size_t gemm_ws_bytes;
+};
+static size_t prefill_ws_layout(const teo_llama_model* m, int T, int B, Arena& A, PrefillWs* w) {
+    const size_t h = m->hidden, I = m->inter;
+    PrefillWs t;
+    t.norm_out = A.take<bf16>(static_cast<size_t>(T) * h);
+    t.qkv = A.take<bf16>(static_cast<size_t>(T) * 3 * h);
+    t.attn = A.take<bf16>(static_cast<size_t>(T) * h);
+    t.gate_up = A.take<bf16>(static_cast<size_t>(T) * 2 * I);
+    t.act = A.take<bf16>(static_cast<size_t>(T) * I);
+    t.last_x = A.take<bf16>(static_cast<size_t>(B) * h);
+    t.last_norm = A.take<bf16>(static_cast<size_t>(B) * h);
+    size_t g = teo_gemm_workspace_bytes(B, m->vocab, m->hidden);
+    g = std::max(g, teo_gemm_workspace_bytes(T, 3 * m->hidden, m->hidden));
+    g = std::max(g, teo_gemm_workspace_bytes(T, 2 * m->inter, m->hidden));
+    g = std::max(g, teo_gemm_workspace_bytes(T, m->hidden, m->inter));
+    t.gemm_ws_bytes = g;
+    t.gemm_ws = A.take<uint8_t>(g);
+    if (w) *w = t;
+    return A.off;
+}
+extern "C" size_t teo_llama_prefill_workspace_bytes(const teo_llama_model* m, int tokens, int n_seqs) {
+    if (!m || tokens <= 0 || n_seqs <= 0) return 0;
+    Arena A(nullptr, 0);
+    return prefill_ws_layout(m, tokens, n_seqs, A, nullptr);
+}
+
+static int llama_layer_mlp(teo_handle* h, const teo_llama_model* m, const teo_llama_layer& L, bf16* x, int rows, bf16* norm_out,
+                           bf16* gate_up, bf16* act, void* gws, size_t gws_bytes, cudaStream_t stream) {
+    const int hd = m->hidden, I = m->inter;
+    TEO_TRY(teo_rmsnorm(x, L.post_norm, norm_out, rows, hd, m->eps, stream));
+    GemmEpilogue none;
+    TEO_TRY(launch_gemm(h, norm_out, hd, static_cast<const bf16*>(L.gate_up_w), hd, gate_up, 2 * I, rows, 2 * I, hd, none, gws, gws_bytes,
+                        stream));
+    TEO_TRY(teo_swiglu(gate_up, act, rows, I, stream));
+    GemmEpilogue res;
+    res.residual = x;
+    res.ldr = hd;
+    TEO_TRY(launch_gemm(h, act, I, static_cast<const bf16*>(L.down_w), I, x, hd, rows, hd, I, res, gws, gws_bytes, stream));
+    h->launches += 2;
+    return TEO_OK;
+}
+
+extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* x_, int tokens, const void* cu_seqlens,
+                                 const void* positions, const void* seq_ids, const void* last_rows, int n_seqs, int max_seqlen,
+                                 const void* block_table, int max_pages, void* logits, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+    TEO_CHECK_ARG(h && m && x_ && cu_seqlens && positions && seq_ids && last_rows && block_table && logits, "llama_prefill: null pointer");
+    TEO_CHECK_ARG(tokens > 0 && n_seqs > 0 && max_seqlen > 0, "llama_prefill: bad sizes");
+    TEO_CHECK_ARG(m->hidden % m->heads == 0 && m->layer != nullptr, "llama_prefill: bad model");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    bf16* x = static_cast<bf16*>(x_);
+    const int hdim = m->hidden, hd = hdim / m->heads;
+    Arena A(workspace, workspace_bytes);
+    PrefillWs w;
+    prefill_ws_layout(m, tokens, n_seqs, A, &w);
+    if (!A.ok) {
+        set_error("llama_prefill: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
+        return TEO_ERR_WORKSPACE;
+    }
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    for (int l = 0; l < m->layers; ++l) {
+        const teo_llama_layer& L = m->layer[l];
+        TEO_TRY(teo_rmsnorm(x, L.in_norm, w.norm_out, tokens, hdim, m->eps, stream));
+        GemmEpilogue none;
+        TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, tokens, 3 * hdim, hdim, none,
+                            w.gemm_ws, w.gemm_ws_bytes, stream));
+        TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(positions), static_cast<const int*>(seq_ids), L.kv_pages,
+                                     static_cast<const int*>(block_table), max_pages, tokens, m->heads, hd, m->page_size,
+                                     static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin), stream));
+        TEO_TRY(launch_flash_attention(w.qkv, 3 * hdim, w.qkv + hdim, 3 * hdim, w.qkv + 2 * hdim, 3 * hdim, w.attn, hdim,
+                                       static_cast<const int*>(cu_seqlens), n_seqs, max_seqlen, m->heads, hd, scale, 1, stream));
+        GemmEpilogue res;
+        res.residual = x;
+        res.ldr = hdim;
+        TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, x, hdim, tokens, hdim, hdim, res, w.gemm_ws,
+                            w.gemm_ws_bytes, stream));
+        h->launches += 3;
+        TEO_TRY(llama_layer_mlp(h, m, L, x, tokens, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
+    }
+    // only the last position of every sequence feeds lm_head (the reference
+    // materialises logits for all positions and discards them)
+    TEO_TRY(teo_splice_embed(x, nullptr, last_rows, w.last_x, n_seqs, hdim, stream));
+    TEO_TRY(teo_rmsnorm(w.last_x, m->final_norm, w.last_norm, n_seqs, hdim, m->eps, stream));
+    GemmEpilogue lg;
+    lg.out_fp32 = 1;
+    TEO_TRY(launch_gemm(h, w.last_norm, hdim, static_cast<const bf16*>(m->lm_head), hdim, logits, m->vocab, n_seqs, m->vocab, hdim, lg,
+                        w.gemm_ws, w.gemm_ws_bytes, stream));
+    h->launches += 2;
+    return TEO_OK;
+}
+
+// ------------------------------------------------------------------------------ LLaMA decode step
+struct DecodeWs {
+    bf16 *x, *norm_out, *qkv, *attn, *gate_up, *act;
+    uint8_t *gemm_ws, *attn_ws;
+    size_t gemm_ws_bytes, attn_ws_bytes;
+};
+static size_t decode_ws_layout(const teo_llama_model* m, int B, Arena& A, DecodeWs* w) {
+    const size_t h = m->hidden, I = m->inter;
+    DecodeWs t;
+    t.x = A.take<bf16>(static_cast<size_t>(B) * h);
+    t.norm_out = A.take<bf16>(static_cast<size_t>(B) * h);
+    t.qkv = A.take<bf16>(static_cast<size_t>(B) * 3 * h);
+    t.attn = A.take<bf16>(static_cast<size_t>(B) * h);
+    t.gate_up = A.take<bf16>(static_cast<size_t>(B) * 2 * I);
+    t.act = A.take<bf16>(static_cast<size_t>(B) * I);
+    size_t g = teo_gemm_workspace_bytes(B, m->vocab, m->hidden);
+    g = std::max(g, teo_gemm_workspace_bytes(B, 3 * m->hidden, m->hidden));
+    g = std::max(g, teo_gemm_workspace_bytes(B, 2 * m->inter, m->hidden));
+    g = std::max(g, teo_gemm_workspace_bytes(B, m->hidden, m->inter));
+    t.gemm_ws_bytes = g;
+    t.gemm_ws = A.take<uint8_t>(g);
+    t.attn_ws_bytes = teo_decode_attention_workspace_bytes(B, m->heads, m->hidden / m->heads, 32);
+    t.attn_ws = A.take<uint8_t>(t.attn_ws_bytes);
+    if (w) *w = t;
+    return A.off;
+}
+extern "C" size_t teo_llama_decode_workspace_bytes(const teo_llama_model* m, int n_seqs, int max_seq_len) {
+    (void)max_seq_len;
+    if (!m || n_seqs <= 0) return 0;
+    Arena A(nullptr, 0);
+    return decode_ws_layout(m, n_seqs, A, nullptr);
+}
+
+extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, void* next_ids, void* seq_lens, void* finished,
+                                     void* tokens, int max_new, void* step_ptr, int n_seqs, int max_seq_len, const void* block_table,
+                                     int max_pages, void* logits, int eos_id, void* workspace, size_t workspace_bytes, void* stream_) {
+    TEO_CHECK_ARG(h && m && next_ids && seq_lens && finished && tokens && step_ptr && block_table && logits, "llama_decode_step: null pointer");
+    TEO_CHECK_ARG(n_seqs > 0 && max_seq_len > 0 && max_new > 0, "llama_decode_step: bad sizes");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int hdim = m->hidden, hd = hdim / m->heads;
+    Arena A(workspace, workspace_bytes);
+    DecodeWs w;
+    decode_ws_layout(m, n_seqs, A, &w);
+    if (!A.ok) {
+        set_error("llama_decode_step: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
+        return TEO_ERR_WORKSPACE;
+    }
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    TEO_TRY(teo_splice_embed(m->embed, nullptr, next_ids, w.x, n_seqs, hdim, stream));
+    h->launches += 1;
+    for (int l = 0; l < m->layers; ++l) {
+        const teo_llama_layer& L = m->layer[l];
+        TEO_TRY(teo_rmsnorm(w.x, L.in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
+        GemmEpilogue none;
+        TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, n_seqs, 3 * hdim, hdim, none,
+                            w.gemm_ws, w.gemm_ws_bytes, stream));
+        // position of the new token = tokens cached so far
+        TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(seq_lens), nullptr, L.kv_pages, static_cast<const int*>(block_table),
+                                     max_pages, n_seqs, m->heads, hd, m->page_size, static_cast<const float*>(m->rope_cos),
+                                     static_cast<const float*>(m->rope_sin), stream));
+        TEO_TRY(launch_decode_attention(h, w.qkv, 3 * hdim, static_cast<const bf16*>(L.kv_pages), static_cast<const int*>(block_table),
+                                        max_pages, static_cast<const int*>(seq_lens), 1, w.attn, n_seqs, m->heads, hd, m->page_size,
+                                        max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
+        GemmEpilogue res;
+        res.residual = w.x;
+        res.ldr = hdim;
+        TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, w.x, hdim, n_seqs, hdim, hdim, res, w.gemm_ws,
+                            w.gemm_ws_bytes, stream));
+        h->launches += 2;
+        TEO_TRY(llama_layer_mlp(h, m, L, w.x, n_seqs, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
+    }
+    TEO_TRY(teo_rmsnorm(w.x, m->final_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
+    GemmEpilogue lg;
+    lg.out_fp32 = 1;
+    TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(m->lm_head), hdim, logits, m->vocab, n_seqs, m->vocab, hdim, lg,
+                        w.gemm_ws, w.gemm_ws_bytes, stream));
+    TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
+                               max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,
+                               eos_id, stream));
+    h->launches += 3;
+    return TEO_OK;
+}

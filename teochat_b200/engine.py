@@ -1,0 +1,377 @@
+"""Batched TEOChat inference engine over the C-ABI kernels.
+
+Replaces, for the inference hot path, the reference's ``LlavaLlamaForCausalLM`` +
+``LlavaMetaForCausalLM`` + HF ``generate`` stack (llava_llama.py:56-108, llava_arch.py:137-346,
+SURVEY.md §3.2): per-frame CLIP-ViT encode → mlp2x_gelu projector → multimodal splice →
+ragged batched LLaMA prefill into a paged KV cache → greedy decode with the whole step captured
+in a CUDA graph (no per-token host synchronisation; the reference syncs every token in
+KeywordsStoppingCriteria, mm_utils.py:94).
+
+PyTorch is used for device memory, streams and CUDA-graph capture only; every FLOP runs in
+teochat_b200/csrc through teochat_b200.lib (ctypes).  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .config import TeoConfig
+from .constants import IMAGE_TOKEN_INDEX
+from .weights import TeoWeights
+
+
+def _cdiv(a: int, b: int) -> int:
+    return (a + b - 1) // b
+
+
+class TeoModel:
+    """Duck-types what the reference's callers touch on ``model``: ``generate``,
+    ``device``, ``config``, ``get_image_tower()``, settable ``model.video_tower``."""
+
+    VIT_CHUNK_FRAMES = 512
+
+    def __init__(self, cfg: TeoConfig, weights: TeoWeights, device=None):
+        if not torch.cuda.is_available():
+            raise L.TeoError("teochat_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.cfg = cfg
+        self.config = cfg                      # reference callers read model.config
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = torch.bfloat16
+        self.w = weights
+        self.lib = L.load()
+        self.model = SimpleNamespace(video_tower=None)     # eval.py:31 sets model.model.video_tower = None
+        h = C.c_void_p()
+        L.check(self.lib.teo_create(self.device.index, C.byref(h)), "teo_create")
+        self._h = h
+        self._ws_cache: Dict[str, torch.Tensor] = {}
+        self._kv_pool: Optional[torch.Tensor] = None
+        self._build_structs()
+        self.use_graph = os.environ.get("TEO_NO_GRAPH", "0") != "1"
+        self.last_timings: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.teo_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def get_image_tower(self):
+        return self
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def launch_count(self) -> int:
+        return int(self.lib.teo_launch_count(self._h))
+
+    def _ws(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._ws_cache.get(name)
+        if t is None or t.numel() < nbytes:
+            if t is not None:
+                del self._ws_cache[name]
+                del t
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws_cache[name] = t
+        return t
+
+    def _build_structs(self):
+        cfg, t = self.cfg, self.w.t
+        v, l = cfg.vision, cfg.llama
+        p = lambda k: t[k].data_ptr()
+        n_run = cfg.vit_layers_run
+        self._vit_layers = (L.VitLayer * max(n_run, 1))()
+        for i in range(n_run):
+            for f, _ in L.VitLayer._fields_:
+                setattr(self._vit_layers[i], f, p(f"vit.{i}.{f}"))
+        self._vit = L.VitModel(hidden=v.hidden_size, inter=v.intermediate_size, heads=v.num_attention_heads,
+                               image=v.image_size, patch=v.patch_size, kpad=self.w.kpad,
+                               act=L.ACT_BY_NAME[v.hidden_act], layers_run=n_run, eps=v.layer_norm_eps,
+                               patch_w=p("vit.patch_w"), cls=p("vit.cls"), pos=p("vit.pos"),
+                               pre_ln_w=p("vit.pre_ln_w"), pre_ln_b=p("vit.pre_ln_b"), layers=self._vit_layers)
+        if cfg.mm_projector_type != "mlp2x_gelu":
+            raise ValueError(f"Unknown projector type: {cfg.mm_projector_type}")   # projector/builder.py:51
+        self._proj = L.Projector(in_dim=v.hidden_size, hidden=l.hidden_size, w0=p("proj.w0"), b0=p("proj.b0"),
+                                 w2=p("proj.w2"), b2=p("proj.b2"))
+        # RoPE tables exactly as HF builds cos_cached/sin_cached (fp32, on the host)
+        hd = l.head_dim
+        self.rope_max_pos = max(l.max_position_embeddings, 8192)
+        inv_freq = 1.0 / (l.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        fr = torch.arange(self.rope_max_pos, dtype=torch.float32)[:, None] * inv_freq[None, :]
+        self._rope_cos = fr.cos().contiguous().to(self.device)
+        self._rope_sin = fr.sin().contiguous().to(self.device)
+        self._llama_layers = (L.LlamaLayer * l.num_hidden_layers)()
+        for i in range(l.num_hidden_layers):
+            for f in ("in_norm", "qkv_w", "o_w", "post_norm", "gate_up_w", "down_w"):
+                setattr(self._llama_layers[i], f, p(f"llama.{i}.{f}"))
+        self._llama = L.LlamaModel(hidden=l.hidden_size, inter=l.intermediate_size, heads=l.num_attention_heads,
+                                   layers=l.num_hidden_layers, vocab=l.vocab_size, page_size=cfg.kv_page_size,
+                                   rope_max_pos=self.rope_max_pos, eps=l.rms_norm_eps,
+                                   rope_cos=self._rope_cos.data_ptr(), rope_sin=self._rope_sin.data_ptr(),
+                                   embed=p("llama.embed"), final_norm=p("llama.final_norm"),
+                                   lm_head=p("llama.lm_head"), layer=self._llama_layers)
+
+    def _ensure_kv(self, n_pages: int):
+        l, ps = self.cfg.llama, self.cfg.kv_page_size
+        if self._kv_pool is None or self._kv_pool.shape[1] < n_pages:
+            self._kv_pool = None
+            self._kv_pool = torch.empty(l.num_hidden_layers, n_pages, 2, l.num_attention_heads, ps, l.head_dim,
+                                        dtype=torch.bfloat16, device=self.device)
+        for i in range(l.num_hidden_layers):
+            self._llama_layers[i].kv_pages = self._kv_pool[i].data_ptr()
+
+    # ------------------------------------------------------------------ vision
+    def encode_images(self, frames_u8: Optional[torch.Tensor] = None, pixel_values: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """encode_images (llava_arch.py:137-140): tower (hidden_states[select_layer], CLS dropped)
+        + projector.  frames_u8: u8 [n,H,W,3] on the device, or pixel_values: f32 [n,3,H,W]
+        (already normalised).  Returns bf16 [n, tokens_per_image, llama_hidden]."""
+        cfg, v = self.cfg, self.cfg.vision
+        if cfg.mm_vision_select_feature != "patch":
+            raise ValueError(f"Unexpected select feature: {cfg.mm_vision_select_feature}")
+        src = frames_u8 if frames_u8 is not None else pixel_values
+        if src is None:
+            raise ValueError("encode_images needs frames_u8 or pixel_values")
+        if frames_u8 is not None:
+            if frames_u8.dtype != torch.uint8 or tuple(frames_u8.shape[1:]) != (v.image_size, v.image_size, 3):
+                raise ValueError(f"frames_u8 must be u8 [n,{v.image_size},{v.image_size},3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+        else:
+            if tuple(pixel_values.shape[1:]) != (3, v.image_size, v.image_size):
+                raise ValueError(f"pixel_values must be [n,3,{v.image_size},{v.image_size}], got {tuple(pixel_values.shape)}")
+            src = pixel_values.to(device=self.device, dtype=torch.float32)
+        src = src.to(self.device).contiguous()
+        n, npch, d, hl = src.shape[0], v.num_patches, v.hidden_size, cfg.llama.hidden_size
+        out = torch.empty(n, npch, hl, dtype=torch.bfloat16, device=self.device)
+        stream = self._stream()
+        for s in range(0, n, self.VIT_CHUNK_FRAMES):
+            c = min(self.VIT_CHUNK_FRAMES, n - s)
+            wsb = self.lib.teo_vit_workspace_bytes(C.byref(self._vit), c)
+            ws = self._ws("vit", wsb)
+            feats = self._ws("vit_feats", c * npch * d * 2)
+            chunk = src[s:s + c]
+            L.check(self.lib.teo_vit_encode(self._h, C.byref(self._vit),
+                                            chunk.data_ptr() if frames_u8 is not None else None,
+                                            None if frames_u8 is not None else chunk.data_ptr(),
+                                            c, feats.data_ptr(), ws.data_ptr(), ws.numel(), stream), "teo_vit_encode")
+            pwb = self.lib.teo_projector_workspace_bytes(C.byref(self._proj), c * npch)
+            pws = self._ws("proj", pwb)
+            L.check(self.lib.teo_projector_mlp2x(self._h, C.byref(self._proj), feats.data_ptr(), c * npch,
+                                                 out[s:s + c].data_ptr(), pws.data_ptr(), pws.numel(), stream),
+                    "teo_projector_mlp2x")
+        return out
+
+    # ------------------------------------------------------------------ splice plan (host, integer)
+    def plan_splice(self, input_ids: Sequence[Sequence[int]], images_per_sample: Sequence[int]):
+        """Index plan of prepare_inputs_labels_for_multimodal (llava_arch.py:251-331) for a ragged
+        batch: for every output row the source (token id ≥ 0, or -(feature_row+1) for image rows),
+        with the reference's truncation to tokenizer_model_max_length (llava_arch.py:296-299)."""
+        tpi = self.cfg.tokens_per_image
+        maxlen = self.cfg.tokenizer_model_max_length
+        srcs, lens = [], []
+        img_base = 0
+        for ids, n_img in zip(input_ids, images_per_sample):
+            ids = np.asarray(list(ids), dtype=np.int64)
+            is_img = ids == IMAGE_TOKEN_INDEX
+            k = int(is_img.sum())
+            if k > n_img:
+                raise IndexError(f"sample has {k} <image> tokens but only {n_img} images")   # llava_arch.py:287 would IndexError
+            bad = (ids < 0) & ~is_img
+            if bad.any() or (ids >= self.cfg.llama.vocab_size).any():
+                raise ValueError("token id outside the vocabulary")
+            reps = np.where(is_img, tpi, 1)
+            starts = np.cumsum(reps) - reps
+            out = np.empty(int(reps.sum()), dtype=np.int64)
+            out[starts[~is_img]] = ids[~is_img]
+            img_ord = np.cumsum(is_img) - 1
+            for pos in np.nonzero(is_img)[0]:
+                r0 = (img_base + int(img_ord[pos])) * tpi
+                out[starts[pos]:starts[pos] + tpi] = -(np.arange(r0, r0 + tpi) + 1)
+            if maxlen is not None:
+                out = out[:maxlen]
+            srcs.append(out)
+            lens.append(len(out))
+            img_base += n_img
+        return srcs, lens
+
+    # ------------------------------------------------------------------ batched generation
+    @torch.no_grad()
+    def generate_batch(self, input_ids: Sequence[Sequence[int]], frames_u8: Optional[Sequence[torch.Tensor]] = None,
+                       pixel_values: Optional[Sequence[torch.Tensor]] = None, max_new_tokens: int = 256,
+                       eos_token_id: Optional[int] = None, return_logits: bool = False, time_phases: bool = False):
+        """Greedy generation for a ragged batch of independent (image sequence, prompt) pairs.
+
+        frames_u8[i]: u8 [T_i,H,W,3] (host or device) — or pixel_values[i]: f32 [T_i,3,H,W].
+        Returns a list of per-sample new-token id lists (eos included if produced), like
+        ``output_ids[0, input_ids.shape[1]:]`` in eval/inference.py:75.
+        """
+        cfg, l = self.cfg, self.cfg.llama
+        B = len(input_ids)
+        if B == 0:
+            return []
+        if max_new_tokens < 1:
+            raise ValueError("max_new_tokens must be >= 1")
+        eos = l.eos_token_id if eos_token_id is None else eos_token_id
+        imgs = frames_u8 if frames_u8 is not None else pixel_values
+        if imgs is None or len(imgs) != B:
+            raise ValueError("need one image stack per sample")
+        dev, stream = self.device, self._stream()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if time_phases else None
+        if ev:
+            ev[0].record()
+        # ---- vision: all frames of the batch in one go
+        per_sample = [int(x.shape[0]) for x in imgs]
+        stacked = torch.cat([x.to(dev, non_blocking=True) for x in imgs], dim=0)
+        proj = self.encode_images(frames_u8=stacked) if frames_u8 is not None else self.encode_images(pixel_values=stacked)
+        if ev:
+            ev[1].record()
+        # ---- splice plan (host integers) → device
+        srcs, lens = self.plan_splice(input_ids, per_sample)
+        T, max_len = int(sum(lens)), int(max(lens))
+        total_len = max_len + max_new_tokens
+        if total_len > self.rope_max_pos:
+            raise ValueError(f"context {total_len} exceeds RoPE table ({self.rope_max_pos})")
+        ps = cfg.kv_page_size
+        pages_per = [_cdiv(n + max_new_tokens, ps) for n in lens]
+        max_pages = max(pages_per)
+        cu = np.zeros(B + 1, dtype=np.int32)
+        cu[1:] = np.cumsum(lens)
+        meta = np.empty(3 * T + (B + 1) + B + B + B * max_pages, dtype=np.int32)
+        o = 0
+        v_src = meta[o:o + T]; o += T
+        v_pos = meta[o:o + T]; o += T
+        v_sid = meta[o:o + T]; o += T
+        v_cu = meta[o:o + B + 1]; o += B + 1
+        v_last = meta[o:o + B]; o += B
+        v_len = meta[o:o + B]; o += B
+        v_bt = meta[o:o + B * max_pages].reshape(B, max_pages); o += B * max_pages
+        v_src[:] = np.concatenate(srcs)
+        v_pos[:] = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
+        v_sid[:] = np.repeat(np.arange(B, dtype=np.int32), lens)
+        v_cu[:] = cu
+        v_last[:] = cu[1:] - 1
+        v_len[:] = lens
+        page0 = 0
+        v_bt[:] = 0
+        for b in range(B):
+            v_bt[b, :pages_per[b]] = np.arange(page0, page0 + pages_per[b], dtype=np.int32)
+            page0 += pages_per[b]
+        self._ensure_kv(page0)
+        meta_h = torch.from_numpy(meta).pin_memory()
+        meta_d = meta_h.to(dev, non_blocking=True)
+        d_src, d_pos, d_sid = meta_d[0:T], meta_d[T:2 * T], meta_d[2 * T:3 * T]
+        o = 3 * T
+        d_cu = meta_d[o:o + B + 1]; o += B + 1
+        d_last = meta_d[o:o + B]; o += B
+        d_len = meta_d[o:o + B].clone(); o += B           # becomes the live seq_lens
+        d_bt = meta_d[o:o + B * max_pages]
+        h = l.hidden_size
+        x = self._ws("x", T * h * 2)
+        L.check(self.lib.teo_splice_embed(self.w.t["llama.embed"].data_ptr(), proj.data_ptr(), d_src.data_ptr(), x.data_ptr(), T, h,
+                                          stream), "teo_splice_embed")
+        logits = torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev)
+        pwb = self.lib.teo_llama_prefill_workspace_bytes(C.byref(self._llama), T, B)
+        pws = self._ws("prefill", pwb)
+        L.check(self.lib.teo_llama_prefill(self._h, C.byref(self._llama), x.data_ptr(), T, d_cu.data_ptr(), d_pos.data_ptr(),
+                                           d_sid.data_ptr(), d_last.data_ptr(), B, max_len, d_bt.data_ptr(), max_pages,
+                                           logits.data_ptr(), pws.data_ptr(), pws.numel(), stream), "teo_llama_prefill")
+        finished = torch.zeros(B, dtype=torch.uint8, device=dev)
+        tokens = torch.full((B, max_new_tokens), -1, dtype=torch.int32, device=dev)
+        next_ids = torch.empty(B, dtype=torch.int32, device=dev)
+        step_ptr = torch.ones(1, dtype=torch.int32, device=dev)
+        L.check(self.lib.teo_argmax_step(logits.data_ptr(), l.vocab_size, finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0,
+                                         next_ids.data_ptr(), B, eos, stream), "teo_argmax_step")
+        step_logits = [logits.clone()] if return_logits else None
+        if ev:
+            ev[2].record()
+        # ---- decode: one captured step, replayed
+        dwb = self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len)
+        dws = self._ws("decode", dwb)
+
+        def step():
+            L.check(self.lib.teo_llama_decode_step(self._h, C.byref(self._llama), next_ids.data_ptr(), d_len.data_ptr(),
+                                                   finished.data_ptr(), tokens.data_ptr(), max_new_tokens, step_ptr.data_ptr(), B,
+                                                   total_len, d_bt.data_ptr(), max_pages, logits.data_ptr(), eos, dws.data_ptr(),
+                                                   dws.numel(), self._stream()), "teo_llama_decode_step")
+
+        n_steps = max_new_tokens - 1
+        graph = None
+        done = 0
+        if n_steps > 0:
+            step()                      # first step eagerly (also warms function attributes / tensor maps)
+            done = 1
+            if return_logits:
+                step_logits.append(logits.clone())
+        if self.use_graph and not return_logits and n_steps - done >= 4:
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.graph(graph, stream=cap_stream):
+                step()
+        while done < n_steps:
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+                if return_logits:
+                    step_logits.append(logits.clone())
+            done += 1
+            if done % 32 == 0 and bool(finished.all()):     # one D2H sync every 32 tokens
+                break
+        if ev:
+            ev[3].record()
+        toks = tokens.cpu().numpy()
+        if ev:
+            torch.cuda.synchronize(dev)
+            self.last_timings = {"vit_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
+                                 "decode_ms": ev[2].elapsed_time(ev[3]), "frames": int(sum(per_sample)),
+                                 "prefill_tokens": T, "decode_steps": done, "batch": B}
+        outs: List[List[int]] = []
+        for b in range(B):
+            row = toks[b]
+            cut = len(row)
+            neg = np.nonzero(row < 0)[0]
+            if len(neg):
+                cut = int(neg[0])
+            outs.append([int(t) for t in row[:cut]])
+        if return_logits:
+            return outs, torch.stack(step_logits, dim=1)     # [B, steps, vocab]
+        return outs
+
+    # ------------------------------------------------------------------ HF-like single-sample API
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor = None, images=None, do_sample: bool = False, temperature: float = 0.0,
+                 max_new_tokens: int = 256, use_cache: bool = True, stopping_criteria=None, **kwargs) -> torch.Tensor:
+        """``model.generate`` as called at eval/inference.py:64-72: ``input_ids`` [1,L] with -200 at
+        image slots, ``images`` a list of T tensors [3,H,W].  Returns [1, L+n] (prompt ids unexpanded,
+        SURVEY.md §8 quirk 6)."""
+        if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
+            raise ValueError("generate expects input_ids of shape [1, L]; use generate_batch for batches")
+        if do_sample and temperature and temperature > 0:
+            raise NotImplementedError("sampling (temperature>0) is SURVEY.md §8(f) row 3; pass temperature=0 for the greedy parity path")
+        eos = self.cfg.llama.eos_token_id
+        if stopping_criteria:
+            for sc in stopping_criteria:
+                if hasattr(sc, "is_eos_only") and not sc.is_eos_only(eos):
+                    raise NotImplementedError("only the eval path's [\"</s>\"] stopping rule runs on the device")
+        if isinstance(images, (list, tuple)):
+            px = torch.stack([im.to(torch.float32) for im in images]) if len(images) else None
+        else:
+            px = images
+        if px is None:
+            raise ValueError("generate needs images (the text-only branch is not part of the TEOChat path)")
+        if px.dim() == 3:
+            px = px[None]
+        ids = input_ids[0].tolist()
+        out = self.generate_batch([ids], pixel_values=[px], max_new_tokens=max_new_tokens)[0]
+        new = torch.tensor(out, dtype=input_ids.dtype, device=input_ids.device)[None]
+        return torch.cat([input_ids, new], dim=1)

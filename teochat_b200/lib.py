@@ -1,0 +1,118 @@
+"""ctypes binding of the C-ABI in include/teochat_b200.h (the product's only compute path).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+OK = 0
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
+ACT_BY_NAME = {"none": ACT_NONE, "quick_gelu": ACT_QUICK_GELU, "gelu": ACT_GELU}
+
+vp = C.c_void_p
+
+
+class TeoError(RuntimeError):
+    pass
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b",
+                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitModel(C.Structure):
+    _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("image", C.c_int),
+                ("patch", C.c_int), ("kpad", C.c_int), ("act", C.c_int), ("layers_run", C.c_int),
+                ("eps", C.c_float), ("patch_w", vp), ("cls", vp), ("pos", vp), ("pre_ln_w", vp),
+                ("pre_ln_b", vp), ("layers", C.POINTER(VitLayer))]
+
+
+class Projector(C.Structure):
+    _fields_ = [("in_dim", C.c_int), ("hidden", C.c_int), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
+
+
+class LlamaLayer(C.Structure):
+    _fields_ = [(n, vp) for n in ("in_norm", "qkv_w", "o_w", "post_norm", "gate_up_w", "down_w", "kv_pages")]
+
+
+class LlamaModel(C.Structure):
+    _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+                ("vocab", C.c_int), ("page_size", C.c_int), ("rope_max_pos", C.c_int), ("eps", C.c_float),
+                ("rope_cos", vp), ("rope_sin", vp), ("embed", vp), ("final_norm", vp), ("lm_head", vp),
+                ("layer", C.POINTER(LlamaLayer))]
+
+
+i, f, sz, u64 = C.c_int, C.c_float, C.c_size_t, C.c_uint64
+_SIGS = {
+    # name: (restype, argtypes)
+    "teo_create": (i, [i, C.POINTER(vp)]),
+    "teo_destroy": (i, [vp]),
+    "teo_last_error": (C.c_char_p, []),
+    "teo_abi_version": (i, []),
+    "teo_launch_count": (C.c_ulonglong, [vp]),
+    "teo_init_normal_hash_bf16": (i, [vp, sz, u64, f, f, vp]),
+    "teo_init_normal_hash_f32": (i, [vp, sz, u64, f, f, vp]),
+    "teo_init_u8_hash": (i, [vp, sz, u64, vp]),
+    "teo_gemm_workspace_bytes": (sz, [i, i, i]),
+    "teo_gemm_bf16": (i, [vp, vp, i, vp, i, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]),
+    "teo_patchify_u8_nhwc": (i, [vp, vp, i, i, i, i, vp]),
+    "teo_patchify_f32_nchw": (i, [vp, vp, i, i, i, i, vp]),
+    "teo_vit_assemble_preln": (i, [vp, vp, vp, vp, vp, vp, i, i, i, f, vp]),
+    "teo_layernorm": (i, [vp, vp, vp, vp, i, i, f, vp]),
+    "teo_vit_drop_cls": (i, [vp, vp, i, i, i, vp]),
+    "teo_flash_attention": (i, [vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, f, i, vp]),
+    "teo_rope_kv_write": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
+    "teo_decode_attention_workspace_bytes": (sz, [i, i, i, i]),
+    "teo_decode_attention": (i, [vp, i, vp, vp, i, vp, vp, i, i, i, i, i, f, vp, sz, vp]),
+    "teo_rmsnorm": (i, [vp, vp, vp, i, i, f, vp]),
+    "teo_swiglu": (i, [vp, vp, i, i, vp]),
+    "teo_splice_embed": (i, [vp, vp, vp, vp, i, i, vp]),
+    "teo_argmax_step": (i, [vp, i, vp, vp, i, i, vp, i, i, vp]),
+    "teo_vit_workspace_bytes": (sz, [C.POINTER(VitModel), i]),
+    "teo_vit_encode": (i, [vp, C.POINTER(VitModel), vp, vp, i, vp, vp, sz, vp]),
+    "teo_projector_workspace_bytes": (sz, [C.POINTER(Projector), i]),
+    "teo_projector_mlp2x": (i, [vp, C.POINTER(Projector), vp, i, vp, vp, sz, vp]),
+    "teo_llama_prefill_workspace_bytes": (sz, [C.POINTER(LlamaModel), i, i]),
+    "teo_llama_prefill": (i, [vp, C.POINTER(LlamaModel), vp, i, vp, vp, vp, vp, i, i, vp, i, vp, vp, sz, vp]),
+    "teo_llama_decode_workspace_bytes": (sz, [C.POINTER(LlamaModel), i, i]),
+    "teo_llama_decode_step": (i, [vp, C.POINTER(LlamaModel), vp, vp, vp, vp, i, vp, i, i, vp, i, vp, i, vp, sz, vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (never build implicitly on a GPU box: the .so travels with the snapshot)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise TeoError(f"{path} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                           "There is no CPU or PyTorch fallback.")
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)          # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != OK:
+        msg = load().teo_last_error().decode("utf-8", "replace")
+        raise TeoError(f"{what or 'teochat_b200 call'} failed ({rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """device (or host) address of a torch tensor, None → NULL"""
+    return None if t is None else t.data_ptr()

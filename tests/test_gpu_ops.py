@@ -1,0 +1,288 @@
+"""GPU parity tests, op level: every CUDA kernel against a plain PyTorch fp32 restatement of the
+same op on the same (bf16-valued) inputs.  Tolerances are stated per test; integer / byte /
+index work is bit-exact."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import bf, gemm, rel_err, rnd, stream
+from teochat_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------ synthetic init (bit-exact vs oracle)
+def test_hash_init_matches_oracle(teo):
+    from oracle import hashinit as H
+    from teochat_b200.weights import hash_scale, tensor_seed
+    lib, _ = teo
+    for name, n, std, mean in [("model.layers.0.self_attn.q_proj.weight", 100003, 0.02, 0.0), ("x.norm", 4096, 0.02, 1.0)]:
+        seed = tensor_seed(1234, name)
+        assert seed == H.tensor_seed(1234, name)
+        out = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+        L.check(lib.teo_init_normal_hash_bf16(out.data_ptr(), n, C.c_uint64(seed), hash_scale(std), mean, stream()))
+        ref = H.hash_normal((n,), seed, std, mean).to(torch.bfloat16)
+        assert torch.equal(out.cpu(), ref)
+        out32 = torch.empty(n, dtype=torch.float32, device=DEV)
+        L.check(lib.teo_init_normal_hash_f32(out32.data_ptr(), n, C.c_uint64(seed), hash_scale(std), mean, stream()))
+        assert torch.equal(out32.cpu(), H.hash_normal((n,), seed, std, mean))
+    u = torch.empty(5000, dtype=torch.uint8, device=DEV)
+    L.check(lib.teo_init_u8_hash(u.data_ptr(), 5000, C.c_uint64(77), stream()))
+    assert torch.equal(u.cpu(), H.hash_u8((5000,), 77))
+
+
+# ------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # (M, N, K) — normal tiles (BN 256/128/64), ragged edges, swap-AB + split-K (M <= 128)
+    (128, 256, 64), (256, 512, 128), (300, 1024, 1024), (257 * 3, 3072, 1024), (1000, 4096, 640),
+    (200, 128, 256), (130, 64, 128), (513, 328, 200),
+    (1, 4096, 4096), (5, 512, 256), (32, 12288, 4096), (32, 4096, 11008), (64, 1024, 512), (100, 32000, 512), (17, 256, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(teo, M, N, K):
+    A, W = bf(rnd(M, K, seed=1)), bf(rnd(N, K, scale=K ** -0.5, seed=2))
+    out = gemm(teo, A, W)
+    ref = A.float() @ W.float().t()
+    assert rel_err(out, ref) < 1e-2          # one bf16 rounding of the output: ≤ 2^-8 relative per element
+    out32 = gemm(teo, A, W, out_fp32=True)
+    assert rel_err(out32, ref) < 2e-5        # fp32 accumulate, order differs from torch
+
+
+@pytest.mark.parametrize("M,N,K", [(514, 1024, 1024), (257, 4096, 1024), (32, 4096, 4096), (3, 512, 256), (100, 768, 320)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_epilogues(teo, M, N, K, act):
+    A, W = bf(rnd(M, K, seed=3)), bf(rnd(N, K, scale=K ** -0.5, seed=4))
+    bias, res = bf(rnd(N, seed=5)), bf(rnd(M, N, seed=6))
+    y = A.float() @ W.float().t() + bias.float()
+    if act == 1:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    out = gemm(teo, A, W, bias=bias, act=act)
+    assert rel_err(out, y) < 1e-2
+    out = gemm(teo, A, W, bias=bias, residual=res, act=act)
+    assert rel_err(out, y + res.float()) < 1e-2
+    # in-place residual (C aliases residual), the way the model uses it
+    x = res.clone()
+    gemm(teo, A, W, bias=bias, residual=x, act=act, C_out=x)
+    assert rel_err(x, y + res.float()) < 1e-2
+
+
+def test_gemm_strided_operands(teo):
+    """q/k/v-style views: leading dimension larger than the logical width."""
+    big = bf(rnd(300, 3 * 256, seed=7))
+    A = big[:, 256:512]
+    W = bf(rnd(512, 256, scale=1 / 16, seed=8))
+    out = gemm(teo, A, W)
+    assert rel_err(out, A.float() @ W.float().t()) < 1e-2
+
+
+def test_gemm_bad_args(teo):
+    lib, h = teo
+    A, W = bf(rnd(8, 60)), bf(rnd(8, 60))
+    out = torch.empty(8, 8, dtype=torch.bfloat16, device=DEV)
+    rc = lib.teo_gemm_bf16(h, A.data_ptr(), 60, W.data_ptr(), 60, out.data_ptr(), 8, 8, 8, 60, None, None, 0, 0, 0, None, 0, stream())
+    assert rc == -1 and b"multiples of 8" in lib.teo_last_error()
+
+
+# ------------------------------------------------------------------ patchify / embeddings / norms
+@pytest.mark.parametrize("image,patch", [(224, 14), (56, 14)])
+def test_patchify(teo, image, patch):
+    from oracle import model as OM
+    lib, _ = teo
+    n, g = 3, image // patch
+    kpad = (3 * patch * patch + 63) // 64 * 64
+    frames = torch.randint(0, 256, (n, image, image, 3), dtype=torch.uint8, device=DEV)
+    out = torch.empty(n * g * g, kpad, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_patchify_u8_nhwc(frames.data_ptr(), out.data_ptr(), n, image, patch, kpad, stream()))
+    px = OM.normalize_u8_nhwc(frames.cpu())                        # [n,3,H,W] f32
+    ref = torch.nn.functional.unfold(px, kernel_size=patch, stride=patch).transpose(1, 2).reshape(n * g * g, -1)
+    assert torch.equal(out[:, :3 * patch * patch].cpu(), ref.to(torch.bfloat16))     # bit-exact
+    assert (out[:, 3 * patch * patch:] == 0).all()
+    out2 = torch.empty_like(out)
+    L.check(lib.teo_patchify_f32_nchw(px.to(DEV).contiguous().data_ptr(), out2.data_ptr(), n, image, patch, kpad, stream()))
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("rows,d", [(7, 128), (257 * 2, 1024), (33, 4096), (5, 256)])
+def test_layernorm_rmsnorm(teo, rows, d):
+    lib, _ = teo
+    x, w, b = bf(rnd(rows, d, scale=2.0, seed=1)), bf(1 + 0.1 * rnd(d, seed=2)), bf(0.1 * rnd(d, seed=3))
+    y = torch.empty_like(x)
+    L.check(lib.teo_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, d, 1e-5, stream()))
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), w.float(), b.float(), 1e-5)
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # one bf16 rounding
+    L.check(lib.teo_rmsnorm(x.data_ptr(), w.data_ptr(), y.data_ptr(), rows, d, 1e-5, stream()))
+    xf = x.float()
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
+def test_vit_assemble_and_drop_cls(teo):
+    lib, _ = teo
+    n, npch, d = 3, 16, 128
+    po, cls, pos = bf(rnd(n * npch, d, seed=1)), bf(rnd(d, seed=2)), bf(rnd(npch + 1, d, seed=3))
+    w, b = bf(1 + 0.1 * rnd(d, seed=4)), bf(0.1 * rnd(d, seed=5))
+    hid = torch.empty(n * (npch + 1), d, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_vit_assemble_preln(po.data_ptr(), cls.data_ptr(), pos.data_ptr(), w.data_ptr(), b.data_ptr(), hid.data_ptr(),
+                                       n, npch, d, 1e-5, stream()))
+    emb = torch.cat([cls.float().expand(n, 1, d), po.float().view(n, npch, d)], 1) + pos.float()[None]
+    ref = torch.nn.functional.layer_norm(emb, (d,), w.float(), b.float(), 1e-5).view(-1, d)
+    assert (hid.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    feats = torch.empty(n, npch, d, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_vit_drop_cls(hid.data_ptr(), feats.data_ptr(), n, npch, d, stream()))
+    assert torch.equal(feats, hid.view(n, npch + 1, d)[:, 1:])
+
+
+def test_swiglu_splice_argmax(teo):
+    lib, _ = teo
+    rows, inter = 37, 512
+    gu = bf(rnd(rows, 2 * inter, scale=2.0, seed=1))
+    out = torch.empty(rows, inter, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_swiglu(gu.data_ptr(), out.data_ptr(), rows, inter, stream()))
+    ref = torch.nn.functional.silu(gu[:, :inter].float()) * gu[:, inter:].float()
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # splice gather: bit-exact copy
+    d = 256
+    E, F = bf(rnd(100, d, seed=2)), bf(rnd(40, d, seed=3))
+    src = torch.tensor([1, 5, -1, -2, -40, 99, 0, -7], dtype=torch.int32, device=DEV)
+    o = torch.empty(len(src), d, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_splice_embed(E.data_ptr(), F.data_ptr(), src.data_ptr(), o.data_ptr(), len(src), d, stream()))
+    ref = torch.stack([E[s] if s >= 0 else F[-(s + 1)] for s in src.tolist()])
+    assert torch.equal(o, ref)
+    # greedy argmax + stop rule: ties → lowest index; finished rows keep emitting eos / pad
+    B, V, max_new = 4, 32000, 8
+    lg = rnd(B, V, seed=4)
+    lg[0, 777] = 50.0; lg[0, 31999] = 50.0          # tie → 777
+    lg[1, 2] = 60.0                                  # eos
+    lg[2, 31999] = 70.0
+    fin = torch.tensor([0, 0, 0, 1], dtype=torch.uint8, device=DEV)
+    toks = torch.full((B, max_new), -1, dtype=torch.int32, device=DEV)
+    nxt = torch.empty(B, dtype=torch.int32, device=DEV)
+    L.check(lib.teo_argmax_step(lg.data_ptr(), V, fin.data_ptr(), toks.data_ptr(), max_new, 3, nxt.data_ptr(), B, 2, stream()))
+    assert toks[:, 3].tolist() == [777, 2, 31999, -1]
+    assert nxt.tolist() == [777, 2, 31999, 2]
+    assert fin.tolist() == [0, 1, 0, 1]
+    assert torch.equal(torch.argmax(lg[2]), torch.tensor(31999, device=DEV))
+
+
+# ------------------------------------------------------------------ RoPE + KV pages
+def _rope_tables(max_pos, hd, theta=10000.0):
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+    fr = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None]
+    return fr.cos().contiguous().to(DEV), fr.sin().contiguous().to(DEV)
+
+
+def _rotate_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat([-x[..., h:], x[..., :h]], -1)
+
+
+def test_rope_kv_write(teo):
+    lib, _ = teo
+    H, hd, ps = 4, 128, 16
+    lens = [5, 37, 16]
+    T, B = sum(lens), len(lens)
+    max_pages = 4
+    n_pages = B * max_pages
+    qkv = bf(rnd(T, 3 * H * hd, seed=1))
+    orig = qkv.clone()
+    pos = torch.cat([torch.arange(n) for n in lens]).to(torch.int32).to(DEV)
+    sid = torch.cat([torch.full((n,), i) for i, n in enumerate(lens)]).to(torch.int32).to(DEV)
+    perm = torch.randperm(n_pages)[: B * max_pages].view(B, max_pages).to(torch.int32).to(DEV)   # scattered pages
+    pages = torch.zeros(n_pages, 2, H, ps, hd, dtype=torch.bfloat16, device=DEV)
+    cos, sin = _rope_tables(64, hd)
+    L.check(lib.teo_rope_kv_write(qkv.data_ptr(), pos.data_ptr(), sid.data_ptr(), pages.data_ptr(), perm.data_ptr(), max_pages, T, H,
+                                  hd, ps, cos.data_ptr(), sin.data_ptr(), stream()))
+    q, k, v = [orig[:, i * H * hd:(i + 1) * H * hd].float().view(T, H, hd) for i in range(3)]
+    c = torch.cat([cos, cos], -1)[pos.long()][:, None]
+    s = torch.cat([sin, sin], -1)[pos.long()][:, None]
+    q_ref, k_ref = bf(q * c + _rotate_half(q) * s), bf(k * c + _rotate_half(k) * s)
+    got_q = qkv[:, :H * hd].view(T, H, hd)
+    got_k = qkv[:, H * hd:2 * H * hd].view(T, H, hd)
+    # fp32 products may be contracted to FMA on the device: allow one bf16 ulp on a few elements
+    assert (got_q.float() - q_ref.float()).abs().max().item() <= 2 ** -7 * q_ref.float().abs().max().item()
+    assert (got_k.float() - k_ref.float()).abs().max().item() <= 2 ** -7 * k_ref.float().abs().max().item()
+    assert torch.equal(qkv[:, 2 * H * hd:], orig[:, 2 * H * hd:])           # v untouched
+    for t in range(T):
+        b, p = int(sid[t]), int(pos[t])
+        page, slot = int(perm[b, p // ps]), p % ps
+        assert torch.equal(pages[page, 0, :, slot], got_k[t])               # cache holds exactly what attention will read
+        assert torch.equal(pages[page, 1, :, slot], orig[t, 2 * H * hd:].view(H, hd))
+
+
+# ------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, scale, causal):
+    """q,k,v [S,H,hd] f32 → [S,H,hd]; mirrors the build's rounding of P to bf16 before PV."""
+    s = torch.einsum("qhd,khd->hqk", q, k) * scale
+    if causal:
+        S = q.shape[0]
+        s = s.masked_fill(torch.ones(S, S, dtype=torch.bool, device=q.device).triu(1)[None], float("-inf"))
+    m = s.amax(-1, keepdim=True)
+    p = torch.exp(s - m)
+    o = torch.einsum("hqk,khd->qhd", p.to(torch.bfloat16).float(), v) / p.sum(-1).transpose(0, 1)[..., None]
+    return o
+
+
+@pytest.mark.parametrize("hd,H,lens,causal", [
+    (64, 16, [257, 257, 257], False),        # ViT block shape
+    (64, 2, [17, 17], False),                # tiny ViT
+    (128, 4, [580], True),                   # config (1) prefill shape
+    (128, 2, [1, 63, 64, 65, 130, 300], True),   # ragged batch with edge lengths
+    (128, 2, [200, 31], False),
+])
+def test_flash_attention(teo, hd, H, lens, causal):
+    lib, _ = teo
+    T = sum(lens)
+    qkv = bf(rnd(T, 3 * H * hd, seed=11))
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    out = torch.empty(T, H * hd, dtype=torch.bfloat16, device=DEV)
+    scale = hd ** -0.5
+    d = H * hd
+    L.check(lib.teo_flash_attention(qkv.data_ptr(), 3 * d, qkv[:, d:].data_ptr(), 3 * d, qkv[:, 2 * d:].data_ptr(), 3 * d,
+                                    out.data_ptr(), d, cu.data_ptr(), len(lens), max(lens), H, hd, scale, int(causal), stream()))
+    o = 0
+    for n in lens:
+        q, k, v = [qkv[o:o + n, i * d:(i + 1) * d].float().view(n, H, hd) for i in range(3)]
+        ref = _attn_ref(q, k, v, scale, causal).reshape(n, d)
+        err = (out[o:o + n].float() - ref).abs().max().item()
+        assert err <= 1.5e-2 * ref.abs().max().item(), (n, err)     # bf16 P and bf16 output rounding
+        o += n
+
+
+@pytest.mark.parametrize("hd,ps,H,lens", [
+    (128, 64, 32, [2151, 580, 64, 65, 1, 4000]),      # forces several KV splits
+    (128, 64, 4, [300] * 40),                         # many sequences → single split
+    (128, 16, 2, [1, 15, 16, 17, 100]),               # tiny-config page size
+])
+def test_decode_attention(teo, hd, ps, H, lens):
+    lib, _ = teo
+    B = len(lens)
+    max_pages = max((n + ps - 1) // ps for n in lens)
+    n_pages = B * max_pages
+    bt = torch.randperm(n_pages).view(B, max_pages).to(torch.int32).to(DEV)
+    pages = bf(rnd(n_pages, 2, H, ps, hd, seed=21))
+    q = bf(rnd(B, 3 * H * hd, seed=22))                 # q rows inside a fused qkv buffer (ldq = 3*H*hd)
+    sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=DEV)
+    wsb = lib.teo_decode_attention_workspace_bytes(B, H, hd, 32)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    scale = hd ** -0.5
+    L.check(lib.teo_decode_attention(q.data_ptr(), 3 * H * hd, pages.data_ptr(), bt.data_ptr(), max_pages, sl.data_ptr(), out.data_ptr(),
+                                     B, H, hd, ps, max(lens), scale, ws.data_ptr(), ws.numel(), stream()))
+    for b, n in enumerate(lens):
+        idx = bt[b, : (n + ps - 1) // ps].long()
+        K = pages[idx, 0].permute(0, 2, 1, 3).reshape(-1, H, hd)[:n].float()     # [n,H,hd]
+        V = pages[idx, 1].permute(0, 2, 1, 3).reshape(-1, H, hd)[:n].float()
+        qq = q[b, : H * hd].float().view(1, H, hd)
+        s = torch.einsum("qhd,khd->hqk", qq, K) * scale
+        p = torch.exp(s - s.amax(-1, keepdim=True))
+        ref = (torch.einsum("hqk,khd->qhd", p.to(torch.bfloat16).float(), V) / p.sum(-1).transpose(0, 1)[..., None]).reshape(-1)
+        err = (out[b].float() - ref).abs().max().item()
+        assert err <= 1.5e-2 * ref.abs().max().item(), (b, n, err)
