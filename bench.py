@@ -1,0 +1,322 @@
+"""Benchmark of the TEOChat inference hot path (contract in the task statement, §④).
+
+    python bench.py [--gpus N --steps K --warmup W]            this build on N B200s
+    python bench.py --impl reference [...]                    the CPU oracle port on the host cores
+
+One "step" = one full pass of the hot path over one batch of synthetic input: ViT encode of all
+frames → projector → splice → ragged prefill → greedy decode of `new` tokens.  Workload at every
+N is BASELINE.json configs[2] per GPU (T=8 frames, bs=32, 256 new tokens; configs[3] is the same
+per-GPU work on 8 GPUs): weak scaling, examples sharded across ranks, one NCCL all-gather of ids
+at the end.  `value` = generated tokens/s with the frames already resident in HBM; `e2e` = the
+same through the public batched API with frames in pinned HOST memory (H2D of the frames and D2H
+of the ids inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "generated_tokens_per_s"
+UNIT = "tokens/s"
+INSTRUCTION = ("This is a sequence of images captured at times: <video> "
+               "What objects or changes can you see across the images?")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_prompt_ids(cfg, n_frames):
+    from teochat_b200.eval.inference import build_prompt
+    from teochat_b200.mm_utils import tokenizer_image_token
+    from teochat_b200.tokenizer import StubTokenizer
+    prompt, _, _ = build_prompt(INSTRUCTION, ["f"] * n_frames)
+    return tokenizer_image_token(prompt, StubTokenizer(cfg.llama.vocab_size))
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_leg(n_frames: int, new_tokens: int, steps: int, warmup: int, seed: int = 1234):
+    """The oracle port (kind "port": the reference cannot be imported/compiled here) on all
+    host cores: fp32, random-init full-size weights, one sequence per step."""
+    import torch
+
+    from oracle import model as OM
+    from oracle import weights as OW
+    from teochat_b200.config import TeoConfig
+    cfg = TeoConfig.full()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, int(os.environ.get("TEO_CPU_THREADS", "32"))))   # fp32 GEMMs stop scaling (and NUMA hurts) past ~32 threads
+    torch.set_num_threads(cores)
+    sd = OW.make_state_dict(cfg, seed, dtype=torch.float32)
+    ids = make_prompt_ids(cfg, n_frames)
+    frames = OW.synthetic_frames_u8(n_frames, cfg.vision.image_size, 11)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        px = OM.normalize_u8_nhwc(frames)
+        toks = OM.generate_greedy(sd, cfg, ids, px, new_tokens, policy="fp32", eos_token_id=None)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    s0 = len(ids) - n_frames + n_frames * cfg.tokens_per_image
+    return {"value": new_tokens / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 sequence x T={n_frames} frame(s), context {s0}, {new_tokens} new tokens, fp32 oracle, "
+                      f"mean of {len(times)} run(s) after {warmup} warm-up",
+            "s_per_sample": t, "vit_frames_per_s": None}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T, new = 1, 2                           # bounded sample per step (full config would take hours on CPU)
+    cb = cpu_reference_leg(T, new, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["s_per_sample"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"T={args.frames} frames, bs={args.batch}/GPU, {args.new_tokens} new tokens (BASELINE configs[2]); "
+                                   "CPU arm timed on a bounded sample of it, see cpu_baseline.sample"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from teochat_b200 import dist as TD
+    from teochat_b200.config import TeoConfig
+    from teochat_b200.engine import TeoModel
+    from teochat_b200.weights import TeoWeights, tensor_seed
+    import ctypes as C
+
+    from teochat_b200 import lib as L
+
+    rank, world, local = TD.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = TeoConfig.tiny() if args.tiny else TeoConfig.full()
+    model = TeoModel(cfg, TeoWeights.from_synthetic(cfg, 1234, dev), dev)
+    B, T, new = args.batch, args.frames, args.new_tokens
+    ids = [make_prompt_ids(cfg, T) for _ in range(B)]
+    S0 = len(ids[0]) - T + T * cfg.tokens_per_image
+    img = cfg.vision.image_size
+    # synthetic frames, distinct per rank/sample, generated on the device then mirrored to pinned host memory
+    frames_dev = torch.empty(B, T, img, img, 3, dtype=torch.uint8, device=dev)
+    L.check(model.lib.teo_init_u8_hash(frames_dev.data_ptr(), frames_dev.numel(), C.c_uint64(tensor_seed(1234 + rank, "frames")),
+                                       torch.cuda.current_stream().cuda_stream))
+    frames_host = frames_dev.cpu().pin_memory()
+    dev_list = [frames_dev[b] for b in range(B)]
+    host_list = [frames_host[b] for b in range(B)]
+    n_total = B * world
+
+    def step(frames):
+        outs = model.generate_batch(ids, frames_u8=frames, max_new_tokens=new, time_phases=True)
+        packed = TD.pack_tokens(outs, B, new, dev)
+        gathered = TD.gather_tokens(packed, n_total)          # the one collective (includes the D2H of the ids)
+        return outs, gathered
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(frames, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.launch_count()
+        phases, gen = [], 0
+        e0.record()
+        for _ in range(k):
+            outs, _ = step(frames)
+            phases.append(dict(model.last_timings))
+            gen += sum(len(o) for o in outs)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            g = torch.tensor([gen], dtype=torch.int64, device=dev)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            gen = int(g.item())
+        return ms, gen, phases, model.launch_count() - l0
+
+    for _ in range(args.warmup):
+        step(dev_list)
+    if args.profile:                       # one device-resident step for ncu launch lists; prints no bench line
+        sync_all()
+        step(dev_list)
+        sync_all()
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "phases_ms": model.last_timings}), flush=True)
+        return
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, gen_dev, ph_dev, launches_eager = timed(dev_list, args.steps)
+    ms_e2e, gen_e2e, ph_e2e, _ = timed(host_list, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # launches: eager calls are counted by the handle; graph replays add (steps-2)·per-step launches
+    per_step = 1 + cfg.llama.num_hidden_layers * 14 + 5          # upper bound of kernels in one decode step
+    replays = sum(max(0, p["decode_steps"] - 1) for p in ph_dev) if model.use_graph else 0
+    gpu_launches = int(launches_eager + replays * per_step)
+
+    roof = decode_attention_roofline(model, cfg, B, S0 + new // 2, dev) if not args.tiny else None
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.tiny:
+        cb = cpu_reference_leg(1, 2, 1, 0)
+
+    if rank == 0:
+        k = args.steps
+        vit_fps = sum(p["frames"] for p in ph_dev) / (sum(p["vit_ms"] for p in ph_dev) / 1e3) * world
+        dec_tps = sum(p["batch"] * p["decode_steps"] for p in ph_dev) / (sum(p["decode_ms"] for p in ph_dev) / 1e3) * world
+        pre_tps = sum(p["prefill_tokens"] for p in ph_dev) / (sum(p["prefill_ms"] for p in ph_dev) / 1e3) * world
+        pk = peaks()
+        vit_flops = 155.3e9 + 10.74e9
+        line = {
+            "metric": METRIC, "value": gen_dev / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": k, "warmup": args.warmup,
+            "ms_per_step": ms_dev / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"T={T} frames x bs={B} per GPU, context {S0}, {new} new tokens, greedy (BASELINE configs[2]/[3])",
+                       "global_batch": n_total, "seq_len": S0 + new, "parallelism": f"dp{world}",
+                       "l2": "working set (13.5 GB weights + KV pages) >> 126 MB L2; no flush needed", "weights": "random-init (hash) bf16"},
+            "vit_frames_per_s": vit_fps, "decode_tokens_per_s": dec_tps, "prefill_tokens_per_s": pre_tps,
+            "phases_ms": {kk: sum(p[kk] for p in ph_dev) / k for kk in ("vit_ms", "prefill_ms", "decode_ms")},
+            "vit_tensor_frac_of_measured_peak": (vit_fps / world) * vit_flops / (pk["bf16_tflops_sustained"] * 1e12),
+            "e2e": {"value": gen_e2e / (ms_e2e / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(frames_host.numel() + 4 * (3 * B * S0 + 3 * B + 1 + B * 64)),
+                    "d2h_bytes_per_step": int(B * new * 4), "ms_per_step": ms_e2e / k},
+            "gpu_launches": gpu_launches, "clocks": clocks, "peaks": pk,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cb:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def decode_attention_roofline(model, cfg, B, S, dev, iters=20):
+    """Dominant kernel of the decode loop: decode_attn_kernel.  Algorithmic bytes per launch =
+    Σ_seq 2(K,V)·heads·head_dim·2 B·S = 16 384·S per sequence per layer (524 288·S
+    per token over 32 layers); timed alone with CUDA events on the launching stream on a KV pool of
+    the benchmark's size (36+ GiB per layer set ≫ L2, so every launch streams from HBM)."""
+    import ctypes as C
+
+    import torch
+
+    from teochat_b200 import lib as L
+    l, ps = cfg.llama, cfg.kv_page_size
+    H, hd = l.num_attention_heads, l.head_dim
+    pages_per = (S + ps - 1) // ps
+    n_layers_resident = 8                      # rotate over 8 layers' pools so consecutive launches never hit L2
+    pool = torch.empty(n_layers_resident, B * pages_per, 2, H, ps, hd, dtype=torch.bfloat16, device=dev)
+    pool.view(-1)[: 1 << 20].normal_()
+    bt = torch.arange(B * pages_per, dtype=torch.int32, device=dev).view(B, pages_per)
+    q = torch.randn(B, 3 * H * hd, device=dev).to(torch.bfloat16)
+    sl = torch.full((B,), S, dtype=torch.int32, device=dev)
+    out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=dev)
+    wsb = model.lib.teo_decode_attention_workspace_bytes(B, H, hd, 32)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(i):
+        L.check(model.lib.teo_decode_attention(q.data_ptr(), 3 * H * hd, pool[i % n_layers_resident].data_ptr(), bt.data_ptr(), pages_per,
+                                               sl.data_ptr(), out.data_ptr(), B, H, hd, ps, S, hd ** -0.5, ws.data_ptr(), ws.numel(), stream))
+    for i in range(4):
+        launch(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    alg_bytes = B * 2 * H * hd * 2 * S
+    pk = peaks()
+    ach = alg_bytes / (ms / 1e3) / 1e9
+    del pool
+    return {"kernel": "decode_attn_kernel<128,64>", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " (burst copy)",
+            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
+            "how": f"bs={B}, S={S}, {iters} launches over 8 rotating layer pools, CUDA events"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="teochat_b200", choices=["teochat_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="examples per GPU")
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--new-tokens", type=int, default=256)
+    ap.add_argument("--tiny", action="store_true", help="tiny config (plumbing check only; not a bench number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="run warm-up + exactly one step and exit (for ncu; not a bench number)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

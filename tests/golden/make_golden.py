@@ -36,7 +36,7 @@ def prompt_ids(cfg, n_frames):
     return tokenizer_image_token(prompt, StubTokenizer(cfg.llama.vocab_size))
 
 
-def run(cfg, seed, samples, max_new, out_path):
+def run(cfg, seed, samples, max_new, out_path, selfnoise=False):
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
     sd = OW.make_state_dict(cfg, seed)
@@ -58,6 +58,18 @@ def run(cfg, seed, samples, max_new, out_path):
             rec[f"absmax_{pol}_{i}"] = logits.abs().amax(dim=-1).numpy()
             rec[f"logits0_{pol}_{i}"] = logits[0, ::LOGIT_STRIDE].numpy()
             print(f"sample {i} policy {pol}: {time.time() - t0:.1f}s tokens {toks}", flush=True)
+    if selfnoise:
+        # Reproducibility floor of the oracle itself: rerun the bf16-policy prefill with a different matmul thread
+        # count (only the fp32 accumulation order changes).  At full size with random-init weights the logits move by
+        # a few percent — the network amplifies last-bit differences — so no implementation can match tighter.
+        torch.set_num_threads(3)
+        ids = rec["ids_0"].tolist()
+        nf, fs = rec["frames_0"].tolist()
+        px = OM.normalize_u8_nhwc(OW.synthetic_frames_u8(nf, cfg.vision.image_size, fs))
+        _, lg = OM.generate_greedy(sd, cfg, ids, px, 1, policy="bf16", return_logits=True)
+        a, b = lg[0, ::LOGIT_STRIDE].numpy(), rec["logits0_bf16_0"]
+        rec["selfnoise_bf16_0"] = np.float64(np.abs(a - b).max() / np.abs(b).max())
+        print("oracle self-noise (3 vs all threads):", rec["selfnoise_bf16_0"], flush=True)
     np.savez_compressed(out_path, **rec)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")
 
@@ -68,6 +80,6 @@ if __name__ == "__main__":
     if which == "tiny":
         run(TeoConfig.tiny(), 1234, [(2, 11), (1, 12), (3, 13), (8, 14)], 24, os.path.join(here, "tiny_generate.npz"))
     elif which == "full":
-        run(TeoConfig.full(), 1234, [(2, 11)], 16, os.path.join(here, "config1_full.npz"))
+        run(TeoConfig.full(), 1234, [(2, 11)], 16, os.path.join(here, "config1_full.npz"), selfnoise=True)
     else:
         raise SystemExit("usage: make_golden.py tiny|full")

@@ -1,0 +1,75 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/teochat_b200.h declares, and fails loudly (no fallback) when asked to compute without one."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from teochat_b200 import build as B
+from teochat_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(B.LIB_PATH):
+        B.build()
+    return L.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "teochat_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(teo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/teochat_b200.h but not exported"
+    assert set(syms) == set(L.EXPORTS), "ctypes signature table and header disagree"
+    assert lib.teo_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # pointer-sized fields, int fields in header order (catches drift between lib.py and the header)
+    assert C.sizeof(L.VitLayer) == 12 * C.sizeof(C.c_void_p)
+    assert C.sizeof(L.LlamaLayer) == 7 * C.sizeof(C.c_void_p)
+    assert [f for f, _ in L.VitModel._fields_][:9] == ["hidden", "inter", "heads", "image", "patch", "kpad", "act", "layers_run", "eps"]
+    assert [f for f, _ in L.LlamaModel._fields_][:10] == ["hidden", "inter", "heads", "layers", "vocab", "page_size", "rope_max_pos", "eps",
+                                                         "rope_cos", "rope_sin"]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly(lib):
+    h = C.c_void_p()
+    rc = lib.teo_create(0, C.byref(h))
+    assert rc != 0 and len(lib.teo_last_error()) > 0
+    from teochat_b200.config import TeoConfig
+    from teochat_b200.engine import TeoModel
+    with pytest.raises(L.TeoError, match="no CPU path"):
+        TeoModel(TeoConfig.tiny(), None, "cuda:0")
+    from teochat_b200.eval.eval import load_model
+    with pytest.raises(ValueError, match="llava"):
+        load_model("some-other-model", None)
+    with pytest.raises(NotImplementedError):
+        load_model("teochat-synthetic", None, load_8bit=True)
+
+
+def test_workspace_queries_are_pure(lib):
+    assert lib.teo_gemm_workspace_bytes(4096, 4096, 4096) == 0            # large M: no split-K scratch
+    assert lib.teo_gemm_workspace_bytes(32, 4096, 4096) == 16 * 32 * 4096 * 4
+    assert lib.teo_decode_attention_workspace_bytes(32, 32, 128, 8) == 32 * 32 * 8 * 130 * 4
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "teochat_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"

@@ -1,0 +1,119 @@
+"""CPU tests of the host-side mirror of the reference glue (prompt, tokenisation, stopping rule,
+processor, config).  Expected strings/ids are written out from the reference templates
+(conversation.py:252-262, inference.py:11-55, mm_utils.py:43-104)."""
+import numpy as np
+import pytest
+import torch
+
+from teochat_b200.config import TeoConfig
+from teochat_b200.constants import IMAGE_TOKEN_INDEX
+from teochat_b200.conversation import SeparatorStyle, conv_templates
+from teochat_b200.eval.inference import build_prompt, extract_bboxes, replace_video_token
+from teochat_b200.mm_utils import KeywordsStoppingCriteria, get_model_name_from_path, tokenizer_image_token
+from teochat_b200.processor import TeoImageProcessor
+from teochat_b200.tokenizer import StubTokenizer
+
+SYSTEM = ("A chat between a curious user and an artificial intelligence assistant. "
+          "The assistant gives helpful, detailed, and polite answers to the user's questions.")
+
+
+def test_v1_prompt_two_style():
+    conv = conv_templates["v1"].copy()
+    conv.append_message(conv.roles[0], "hello <video>")
+    conv.append_message(conv.roles[1], None)
+    assert conv.get_prompt() == SYSTEM + " USER: hello <video> ASSISTANT:"
+    assert conv.sep_style == SeparatorStyle.TWO and conv.sep2 == "</s>"
+    conv.messages[-1][1] = "fine"
+    conv.append_message(conv.roles[0], "again")
+    assert conv.get_prompt() == SYSTEM + " USER: hello <video> ASSISTANT: fine</s>USER: again "
+    assert conv_templates["v1"].messages == []          # templates are not mutated by copies
+
+
+def test_replace_video_token_and_build_prompt():
+    assert replace_video_token("a <video> b", ["x", "y"], None) == "a <image><image> b"
+    assert replace_video_token("a <video> b", ["x", "y"], "interleave") == "a Image 1: <image>Image 2: <image> b"
+    with pytest.raises(ValueError, match="Unknown prompt strategy"):
+        replace_video_token("a", ["x"], "zip")
+    prompt, paths, stop = build_prompt("images at times: <video> Q?", ["late", "early"], timestamps=["2021-06-01", "2019-01-31"])
+    assert paths == ["early", "late"]                     # chronological sort (inference.py:45-50)
+    assert "times in chronological order: Image 1: <image>Image 2: <image> Q?" in prompt
+    assert stop == "</s>"
+    p2, _, _ = build_prompt("images at times: <video>", ["a"], chronological_prefix=False)
+    assert "times: Image 1: <image>" in p2
+
+
+def test_tokenizer_image_token():
+    tok = StubTokenizer()
+    ids = tokenizer_image_token("hello world<image>foo<image>", tok)
+    a, b = tok("hello world").input_ids, tok("foo").input_ids
+    assert a[0] == tok.bos_token_id
+    assert ids == a + [IMAGE_TOKEN_INDEX] + b[1:] + [IMAGE_TOKEN_INDEX]        # single BOS, -200 between chunks
+    t = tokenizer_image_token("x<image>y", tok, return_tensors="pt")
+    assert t.dtype == torch.long and t.tolist().count(IMAGE_TOKEN_INDEX) == 1
+    with pytest.raises(ValueError):
+        tokenizer_image_token("x", tok, return_tensors="np")
+
+    class NoBos(StubTokenizer):
+        def __call__(self, text, **kw):
+            r = super().__call__(text)
+            r.input_ids = r.input_ids[1:]
+            return r
+    nb = NoBos()
+    assert tokenizer_image_token("a<image>b", nb) == nb("a").input_ids + [IMAGE_TOKEN_INDEX] + nb("b").input_ids
+
+
+def test_keywords_stopping_criteria():
+    tok = StubTokenizer()
+    prompt = torch.tensor([tok("some prompt").input_ids])
+    sc = KeywordsStoppingCriteria(["</s>"], tok, prompt)
+    assert sc.is_eos_only(tok.eos_token_id)
+    assert not sc(torch.cat([prompt, torch.tensor([[77]])], 1), None)
+    assert sc(torch.cat([prompt, torch.tensor([[77, tok.eos_token_id]])], 1), None)
+    sc2 = KeywordsStoppingCriteria(["stop"], tok, prompt)
+    assert not sc2.is_eos_only(tok.eos_token_id)
+    gen = torch.tensor([tok("go stop").input_ids[1:]])
+    assert sc2(torch.cat([prompt, gen], 1), None)
+
+
+def test_misc_helpers():
+    assert get_model_name_from_path("/a/b/teochat-7b/") == "teochat-7b"
+    assert get_model_name_from_path("/a/teochat/checkpoint-100") == "teochat_checkpoint-100"
+    assert extract_bboxes("see [1, 2, 30, 40] and [5, 6, 7, 8]") == [[1, 2, 30, 40], [5, 6, 7, 8]]
+
+
+def test_processor_matches_torchvision():
+    from PIL import Image
+    from torchvision import transforms
+
+    from teochat_b200.constants import OPENAI_DATASET_MEAN, OPENAI_DATASET_STD
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Resize(224, interpolation=transforms.InterpolationMode.BICUBIC),
+                             transforms.CenterCrop(224), transforms.Normalize(OPENAI_DATASET_MEAN, OPENAI_DATASET_STD)])
+    p = TeoImageProcessor()
+    assert p.crop_size == {"height": 224, "width": 224} and p.image_mean == OPENAI_DATASET_MEAN
+    rng = np.random.RandomState(0)
+    for shape in [(224, 224), (300, 256), (256, 341), (225, 400)]:
+        img = Image.fromarray(rng.randint(0, 256, (shape[0], shape[1], 3), dtype=np.uint8))
+        out = p.preprocess(img, return_tensors="pt")["pixel_values"]
+        assert out.shape == (1, 3, 224, 224)
+        assert torch.equal(out[0], tf(img))
+    with pytest.raises(ValueError):
+        p(images=None)
+    u8 = p.to_uint8_nhwc([rng.randint(0, 256, (224, 224, 3), dtype=np.uint8)] * 2)
+    assert u8.shape == (2, 224, 224, 3) and u8.dtype == torch.uint8
+    with pytest.raises(ValueError):
+        p.to_uint8_nhwc(rng.randint(0, 256, (100, 224, 3), dtype=np.uint8))
+
+
+def test_config_derived_values():
+    cfg = TeoConfig.full()
+    assert cfg.vit_layers_run == 23 and cfg.tokens_per_image == 256 and cfg.vision.patch_dim == 588
+    assert cfg.llama.head_dim == 128 and cfg.vision.head_dim == 64
+    cfg.mm_vision_select_layer = -1
+    assert cfg.vit_layers_run == 24
+    cfg.mm_vision_select_layer = 30
+    with pytest.raises(ValueError):
+        _ = cfg.vit_layers_run
+    cfg = TeoConfig.full()
+    cfg.mm_vision_select_feature = "bogus"
+    with pytest.raises(ValueError, match="Unexpected select feature"):
+        _ = cfg.tokens_per_image
