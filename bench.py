@@ -198,8 +198,10 @@ def run_gpu(args):
         step(dev_list)
     if args.profile:                       # one device-resident step for ncu launch lists; prints no bench line
         sync_all()
+        torch.cuda.profiler.start()            # ncu --profile-from-start off: only this step is captured
         step(dev_list)
         sync_all()
+        torch.cuda.profiler.stop()
         if rank == 0:
             print(json.dumps({"profile_only": True, "phases_ms": model.last_timings}), flush=True)
         return

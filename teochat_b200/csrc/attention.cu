@@ -13,6 +13,8 @@
 //     shared-memory ring signalled by mbarriers, and does the dot products on CUDA cores
 //     (MHA: one query row per KV head, nothing for tensor cores to reuse).  Split partials are
 //     merged by decode_combine_kernel.
+#include <cmath>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -379,12 +381,24 @@ __global__ void decode_combine_kernel(const float* __restrict__ o_part, const fl
     }
 }
 
-static int decode_splits(int n_seqs, int n_heads, int max_seq_len, int page_size, int num_sms) {
+// KV splits per (sequence, head).  All CTAs of a launch carry about the same work, so the launch
+// runs in whole waves of (SMs × resident CTAs): pick the smallest split count whose last wave is
+// ≥ 95 % full (bs=32 × 32 heads = 1024 CTAs over 444 slots is 2.31 waves → 77 % efficient; 3 splits
+// give 6.92 waves → 99 %), keeping ≥ 4 pages per split.
+static int decode_splits(int n_seqs, int n_heads, int max_seq_len, int page_size, int num_sms, int ctas_per_sm) {
     const int ctas = n_seqs * n_heads;
     const int pages = (max_seq_len + page_size - 1) / page_size;
-    int want = (num_sms * 6 + ctas - 1) / ctas;             // ≥ ~2 waves at 3 CTAs/SM
-    want = std::min(want, std::max(1, pages / 4));          // ≥ 4 pages per split
-    return std::max(1, std::min(want, 32));
+    const int slots = num_sms * ctas_per_sm;
+    const int max_s = std::max(1, std::min(32, pages / 4));
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= max_s; ++s) {
+        const double waves = static_cast<double>(ctas) * s / slots;
+        const double eff = waves / std::ceil(waves);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        if (eff >= 0.95) { best = s; break; }
+    }
+    return best;
 }
 
 template <int HD, int PAGE>
@@ -416,7 +430,9 @@ int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* k
     TEO_CHECK_ARG(q && kv_pages && block_table && seq_lens && out, "decode_attention: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && n_heads > 0 && max_seq_len > 0, "decode_attention: bad sizes");
     const int num_sms = h ? h->num_sms : 148;
-    int splits = decode_splits(n_seqs, n_heads, max_seq_len, page_size, num_sms);
+    const int smem_per_cta = 4 * page_size * head_dim * 2 + (head_dim + page_size + (DEC_THREADS / (head_dim / 8)) * head_dim) * 4 + 144;
+    const int ctas_per_sm = std::max(1, std::min(16, (227 * 1024) / (smem_per_cta + 1024)));
+    int splits = decode_splits(n_seqs, n_heads, max_seq_len, page_size, num_sms, ctas_per_sm);
     float *o_part = nullptr, *ml_part = nullptr;
     if (splits > 1) {
         const size_t need = teo_decode_attention_workspace_bytes(n_seqs, n_heads, head_dim, splits);

@@ -6,8 +6,13 @@
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (UMMA 128×BN×16, cta_group::1),
 //                              accumulating in TMEM; tcgen05.commit releases ring slots
 //   warp 2      TMEM allocator (2 accumulator stages × BN fp32 columns)
-//   warps 4-7   epilogue       tcgen05.ld 32 lanes × 32 columns → bias / activation / residual →
-//                              bf16 (or fp32) stores; overlaps the next tile's MMAs
+//   warps 4-11  epilogue       two warps per TMEM lane quadrant (column halves).  bf16 outputs:
+//                              tcgen05.ld 32 lanes × 64 columns → bias / activation / residual
+//                              (residual tile fetched by TMA into the staging buffer) → bf16 →
+//                              128-byte-swizzled staging in shared memory → TMA store (full
+//                              128-byte lines, edges clipped by the tensor map); overlaps the next
+//                              tile's MMAs through the second TMEM accumulator stage.
+//                              fp32 / split-K partial / transposed outputs use direct stores.
 //
 // Schedules:
 //   normal      A = activations [M,K], W = weights [N,K]; tiles 128 × 256
@@ -33,7 +38,9 @@ constexpr int BM = 128;         // UMMA M
 constexpr int BK = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;     // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int STAGING_BYTES = EPI_WARPS * 4096;   // per warp: 32 rows × 64 bf16 (128 B, swizzled)
 constexpr int GROUP_M = 16;     // rasterisation group (tiles along M sharing W tiles in L2)
 
 struct GemmArgs {
@@ -49,6 +56,7 @@ struct GemmArgs {
     int splits;                 // split-K factor; > 1 → fp32 partials, no bias/act/residual here
     long long split_stride;     // elements between partials
     int kb_per_split;           // K blocks per split
+    int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
 };
 
 template <int BN>
@@ -57,11 +65,11 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == TEO_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+    if (act == TEO_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
     if (act == TEO_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     return x;
 }
@@ -81,18 +89,21 @@ __device__ __forceinline__ void unit_to_tile(int unit, const GemmArgs& g, int nu
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs g) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;               // 1024-byte aligned (stage sizes are)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;                                 // [EPI_WARPS] residual tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -104,6 +115,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (g.tma_epi) {
+            tma_prefetch_desc(&tma_c);
+            tma_prefetch_desc(&tma_r);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -112,8 +127,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 128);
+            mbar_init(&tempty_bar[s], EPI_WARPS * 32);
         }
+        for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -178,7 +194,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
-        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int ew = warp - 4;                 // 0..7
+        const int q = ew & 3;                    // TMEM lane quadrant this warp may access (= warp % 4)
+        const int hsel = ew >> 2;                // which column chunks of the tile this warp owns
+        uint8_t* stg = staging + ew * 4096;
+        uint64_t* rbar = &res_bar[ew];
+        uint32_t rph = 0;
         int as = 0;
         uint32_t aph = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -186,86 +207,155 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
-            const int m = m_blk * BM + q * 32 + lane;
-            const bool m_ok = m < g.M;
-            const bool partial = g.splits > 1;
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            if (g.tma_epi) {
+                // ---- staged path: 64-column chunks → swizzled smem → TMA store
+                const int row0 = m_blk * BM + q * 32;
+                const bool has_res = g.residual != nullptr;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int n0 = n_blk * BN + c0;
-                if (n0 >= g.N) break;            // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0, v);
-                tmem_ld_wait();
-                if (g.transposed) {
-                    // C[n, m]: lanes hold consecutive m → coalesced along m for each n
-                    if (partial) {
-                        float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (m_ok && n0 + j < g.N) P[static_cast<long long>(n0 + j) * g.ldc + m] = __uint_as_float(v[j]);
-                    } else {
-                        const float bm = (g.bias && m_ok) ? __bfloat162float(g.bias[m]) : 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (m_ok && n0 + j < g.N) {
-                                float x = apply_act(__uint_as_float(v[j]) + bm, g.act);
-                                if (g.residual) x += __bfloat162float(g.residual[static_cast<long long>(n0 + j) * g.ldr + m]);
-                                const long long o = static_cast<long long>(n0 + j) * g.ldc + m;
-                                if (g.out_fp32) reinterpret_cast<float*>(g.C)[o] = x;
-                                else reinterpret_cast<bf16*>(g.C)[o] = __float2bfloat16_rn(x);
-                            }
+                for (int cj = hsel; cj < BN / 64; cj += 2) {
+                    const int n0 = n_blk * BN + cj * 64;
+                    if (n0 >= g.N) break;                      // warp-uniform
+                    if (lane == 0) {
+                        tma_store_wait_read<0>();              // previous store has drained the staging buffer
+                        if (has_res) {
+                            mbar_arrive_expect_tx(rbar, 4096);
+                            tma_load_2d(stg, &tma_r, rbar, n0, row0);
                         }
                     }
-                } else if (m_ok) {
-                    // row m, 32 consecutive columns n0..n0+31 (N % 8 == 0 → 8-column groups are all-in or all-out)
-                    if (partial) {
-                        float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride +
-                                   static_cast<long long>(m) * g.ldc + n0;
+                    __syncwarp();
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(t_acc + cj * 64, v0);
+                    tmem_ld_32x32(t_acc + cj * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (cj + 2 >= BN / 64 || n0 + 128 >= g.N) {   // last chunk of this warp: accumulator stage is free
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[as]);
+                    }
+                    if (has_res) {
+                        mbar_wait(rbar, rph);
+                        rph ^= 1;
+                    }
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (n0 + j < g.N)
-                                *reinterpret_cast<float4*>(P + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    } else {
+                    for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
+                        float x[8];
 #pragma unroll
-                        for (int j0 = 0; j0 < 32; j0 += 8) {
-                            if (n0 + j0 >= g.N) break;
-                            float x[8];
+                        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
+                        const int n = n0 + c * 8;
+                        if (g.bias && n < g.N) {
+                            const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n);
+                            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j0 + j]);
-                            if (g.bias) {
-                                const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n0 + j0);
-                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+                        }
+                        if (g.act != TEO_ACT_NONE) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+                            for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
+                        }
+                        uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
+                        if (has_res) {
+                            const uint4 rv = *slot;
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
+                        }
+                        *slot = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                           pack_bf16x2(x[6], x[7]));
+                    }
+                    fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tma_c, stg, n0, row0);
+                        tma_store_commit();
+                    }
+                }
+                if (hsel >= BN / 64 || n_blk * BN + hsel * 64 >= g.N) {   // this warp owned no chunk of the tile
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                }
+            } else {
+                // ---- direct path: fp32 / split-K partial / transposed (swap-AB) outputs
+                const int m = m_blk * BM + q * 32 + lane;
+                const bool m_ok = m < g.M;
+                const bool partial = g.splits > 1;
+#pragma unroll 1
+                for (int c0 = hsel * 32; c0 < BN; c0 += 64) {
+                    const int n0 = n_blk * BN + c0;
+                    if (n0 >= g.N) break;            // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + c0, v);
+                    tmem_ld_wait();
+                    if (g.transposed) {
+                        // C[n, m]: lanes hold consecutive m → coalesced along m for each n
+                        if (partial) {
+                            float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (m_ok && n0 + j < g.N) P[static_cast<long long>(n0 + j) * g.ldc + m] = __uint_as_float(v[j]);
+                        } else {
+                            const float bm = (g.bias && m_ok) ? __bfloat162float(g.bias[m]) : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (m_ok && n0 + j < g.N) {
+                                    float x = apply_act(__uint_as_float(v[j]) + bm, g.act);
+                                    if (g.residual) x += __bfloat162float(g.residual[static_cast<long long>(n0 + j) * g.ldr + m]);
+                                    const long long o = static_cast<long long>(n0 + j) * g.ldc + m;
+                                    if (g.out_fp32) reinterpret_cast<float*>(g.C)[o] = x;
+                                    else reinterpret_cast<bf16*>(g.C)[o] = __float2bfloat16_rn(x);
+                                }
                             }
-                            if (g.act != TEO_ACT_NONE) {
+                        }
+                    } else if (m_ok) {
+                        if (partial) {
+                            float* P = reinterpret_cast<float*>(g.C) + static_cast<long long>(split) * g.split_stride +
+                                       static_cast<long long>(m) * g.ldc + n0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
-                            }
-                            if (g.residual) {
-                                const uint4 rv = *reinterpret_cast<const uint4*>(g.residual + static_cast<long long>(m) * g.ldr + n0 + j0);
-                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                            for (int j = 0; j < 32; j += 4)
+                                if (n0 + j < g.N)
+                                    *reinterpret_cast<float4*>(P + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        } else {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
-                            }
-                            if (g.out_fp32) {
-                                float* o = reinterpret_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
-                                *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-                                *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                            } else {
-                                bf16* o = reinterpret_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
-                                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                                                                          pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                            for (int j0 = 0; j0 < 32; j0 += 8) {
+                                if (n0 + j0 >= g.N) break;
+                                float x[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[j0 + j]);
+                                if (g.bias) {
+                                    const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n0 + j0);
+                                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+                                }
+                                if (g.act != TEO_ACT_NONE) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
+                                }
+                                if (g.residual) {
+                                    const uint4 rv = *reinterpret_cast<const uint4*>(g.residual + static_cast<long long>(m) * g.ldr + n0 + j0);
+                                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
+                                }
+                                if (g.out_fp32) {
+                                    float* o = reinterpret_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
+                                    *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+                                    *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                                } else {
+                                    bf16* o = reinterpret_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + n0 + j0;
+                                    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                                                                              pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                                }
                             }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (g.tma_epi && lane == 0) tma_store_wait_all<0>();   // all output tiles written before the CTA retires
     }
 
     tc_fence_before();
@@ -381,8 +471,8 @@ extern "C" size_t teo_gemm_workspace_bytes(int M, int N, int K) {
 }
 
 template <int BN>
-static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& g, int units,
-                      cudaStream_t stream) {
+static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* tb, const CUtensorMap* tc, const CUtensorMap* tr,
+                      const GemmArgs& g, int units, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -390,7 +480,7 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
         attr_set = true;
     }
     const int grid = std::min(units, h->num_sms);
-    gemm_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, g);
+    gemm_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, *tc, *tr, g);
     TEO_LAUNCH_CHECK("gemm_tn_kernel");
     h->launches++;
     return TEO_OK;
@@ -420,7 +510,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     g.K = K;
     g.splits = p.splits;
     g.kb_per_split = p.kb_per_split;
-    const CUtensorMap *ta, *tb;
+    const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr;
     if (p.swap) {
         g.M = N;   // weight rows on the UMMA M dimension
         g.N = M;
@@ -443,14 +533,21 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         g.transposed = 0;
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, BM, &ta));
         TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
+        if (!ep.out_fp32) {           // staged TMA-store epilogue: 32-row × 64-column boxes of C (and of the residual)
+            g.tma_epi = 1;
+            TEO_TRY(get_tmap_bf16(h, C, M, N, ldc, 32, &tc));
+            tr = tc;
+            if (ep.residual) TEO_TRY(get_tmap_bf16(h, ep.residual, M, N, ep.ldr, 32, &tr));
+        }
     }
+    if (!g.tma_epi) tc = tr = ta;     // unused by the direct-store epilogue
     const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
     int rc;
     switch (p.bn) {
-        case 32: rc = launch_cfg<32>(h, ta, tb, g, units, stream); break;
-        case 64: rc = launch_cfg<64>(h, ta, tb, g, units, stream); break;
-        case 128: rc = launch_cfg<128>(h, ta, tb, g, units, stream); break;
-        default: rc = launch_cfg<256>(h, ta, tb, g, units, stream); break;
+        case 32: rc = launch_cfg<32>(h, ta, tb, tc, tr, g, units, stream); break;
+        case 64: rc = launch_cfg<64>(h, ta, tb, tc, tr, g, units, stream); break;
+        case 128: rc = launch_cfg<128>(h, ta, tb, tc, tr, g, units, stream); break;
+        default: rc = launch_cfg<256>(h, ta, tb, tc, tr, g, units, stream); break;
     }
     TEO_TRY(rc);
     if (p.swap && p.splits > 1) {

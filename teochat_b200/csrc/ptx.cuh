@@ -76,6 +76,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
         ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// 2-D tiled store shared→global (bulk async group; out-of-bounds part of the box is clipped).
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(desc), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {   // source smem of all but the last N groups may be reused
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {    // writes of all but the last N groups are complete
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // 1-D bulk copy global→shared (contiguous bytes, multiple of 16), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(
