@@ -132,6 +132,15 @@ int teo_splice_embed(const void* embed_tokens, const void* image_feats, const vo
 int teo_argmax_step(const void* logits, int vocab, void* finished, void* tokens, int max_new, int step,
                     void* next_ids, int n_seqs, int eos_id, void* stream);
 
+/* sampling step (HF sample(): TemperatureLogitsWarper + TopKLogitsWarper + multinomial — the branch
+ * eval/inference.py:64-72 takes with do_sample=True, temperature=0.2 and HF's default top_k=50).
+ * Same state arguments as teo_argmax_step; u comes from a counter-based generator keyed by
+ * (seed, step, sequence): reproducible and graph-replayable, not torch's RNG stream.  top_k <= 0 → no filter. */
+int teo_sample_step(const void* logits, int vocab, float temperature, int top_k, uint64_t seed, void* finished,
+                    void* tokens, int max_new, int step, void* next_ids, int n_seqs, int eos_id, void* stream);
+/* select how teo_llama_decode_step picks the next token for this handle: temperature <= 0 → greedy */
+int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed);
+
 /* ---- whole-model entry points ---------------------------------------------------------- */
 typedef struct {
     const void *ln1_w, *ln1_b;   /* [d] */

@@ -75,6 +75,9 @@ struct teo_handle {
     int device = 0;
     int num_sms = 148;
     unsigned long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
+    float temperature = 0.f;           // > 0 → teo_llama_decode_step samples (teo_set_sampling)
+    int top_k = 50;
+    unsigned long long sample_seed = 0;
     std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
 };
 
@@ -97,5 +100,9 @@ struct GemmEpilogue {
 // workspace: teo_gemm_workspace_bytes(M,N,K) bytes (only used by the split-K schedule).
 int launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
                 const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// Small-M (decode) GEMM that stops at fp32 split-K partials P[s][M][N]; the consumer kernel reduces them.
+int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
+                         size_t workspace_bytes, int* splits_out, cudaStream_t stream);
 
 }  // namespace teo

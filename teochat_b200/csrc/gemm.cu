@@ -57,6 +57,7 @@ struct GemmArgs {
     long long split_stride;     // elements between partials
     int kb_per_split;           // K blocks per split
     int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
+    int force_partial;          // write fp32 partials even when splits == 1
 };
 
 template <int BN>
@@ -277,7 +278,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // ---- direct path: fp32 / split-K partial / transposed (swap-AB) outputs
                 const int m = m_blk * BM + q * 32 + lane;
                 const bool m_ok = m < g.M;
-                const bool partial = g.splits > 1;
+                const bool partial = g.splits > 1 || g.force_partial;
 #pragma unroll 1
                 for (int c0 = hsel * 32; c0 < BN; c0 += 64) {
                     const int n0 = n_blk * BN + c0;
@@ -483,6 +484,44 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
     gemm_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, *tc, *tr, g);
     TEO_LAUNCH_CHECK("gemm_tn_kernel");
     h->launches++;
+    return TEO_OK;
+}
+
+// Small-M GEMM that stops at the fp32 split-K partials: P[s][M][N] in `workspace`, s < *splits_out.
+// The caller's next kernel reduces them (fused with its own work) in the fixed order s = 0,1,...
+int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
+                              size_t workspace_bytes, int* splits_out, cudaStream_t stream) {
+    TEO_CHECK_ARG(h != nullptr && splits_out != nullptr, "gemm_partials: null handle");
+    TEO_CHECK_ARG(M > 0 && M <= 128 && N >= 256 && K > 0 && K % 8 == 0, "gemm_partials: needs 0 < M <= 128, N >= 256, K %% 8 == 0");
+    const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
+    const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("gemm_partials: need %zu workspace bytes, got %zu", need, workspace_bytes);
+        return TEO_ERR_WORKSPACE;
+    }
+    GemmArgs g{};
+    g.M = N;
+    g.N = M;
+    g.K = K;
+    g.transposed = 1;
+    g.splits = p.splits;
+    g.kb_per_split = p.kb_per_split;
+    g.force_partial = 1;
+    g.C = workspace;
+    g.ldc = N;
+    g.split_stride = static_cast<long long>(M) * N;
+    const CUtensorMap *ta, *tb;
+    TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
+    TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
+    const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
+    int rc;
+    switch (p.bn) {
+        case 32: rc = launch_cfg<32>(h, ta, tb, ta, ta, g, units, stream); break;
+        case 64: rc = launch_cfg<64>(h, ta, tb, ta, ta, g, units, stream); break;
+        default: rc = launch_cfg<128>(h, ta, tb, ta, ta, g, units, stream); break;
+    }
+    TEO_TRY(rc);
+    *splits_out = p.splits;
     return TEO_OK;
 }
 

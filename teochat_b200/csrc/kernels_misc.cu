@@ -1,6 +1,8 @@
 // HBM-bound helper kernels of the hot path: synthetic init, patchify (normalise + im2col),
 // embeddings + LayerNorm, RMSNorm, SwiGLU, RoPE + KV-page scatter, splice gather, greedy argmax.
 // All are one-pass, 16-byte-vectorised where the layout allows, fp32 math on bf16 storage.
+#include <cooperative_groups.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -283,6 +285,181 @@ __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restri
         *reinterpret_cast<uint32_t*>(vdst + i) = *reinterpret_cast<const uint32_t*>(v + i);
 }
 
+// ------------------------------------------------------------------------------ decode-step fusions
+// The decode GEMMs (M = batch) leave fp32 split-K partials P[s][rows][n]; these kernels reduce them in the
+// fixed order s = 0,1,… and do the next element-wise stage in the same pass (same rounding points as the
+// unfused chain: the reduced value is rounded to bf16 exactly where the GEMM epilogue would have).
+// Σ_s P[s][idx] in the fixed order s = 0,1,…; loads are issued four at a time so the L2 latencies overlap.
+__device__ __forceinline__ float sum_partials(const float* __restrict__ P, long long stride, int splits, long long idx) {
+    float acc = 0.f;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+        const float p0 = P[(s + 0) * stride + idx], p1 = P[(s + 1) * stride + idx];
+        const float p2 = P[(s + 2) * stride + idx], p3 = P[(s + 3) * stride + idx];
+        acc += p0; acc += p1; acc += p2; acc += p3;
+    }
+    for (; s < splits; ++s) acc += P[s * stride + idx];
+    return acc;
+}
+__device__ __forceinline__ float4 sum_partials4(const float* __restrict__ P, long long stride, int splits, long long idx) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+        const float4 p0 = *reinterpret_cast<const float4*>(P + (s + 0) * stride + idx);
+        const float4 p1 = *reinterpret_cast<const float4*>(P + (s + 1) * stride + idx);
+        const float4 p2 = *reinterpret_cast<const float4*>(P + (s + 2) * stride + idx);
+        const float4 p3 = *reinterpret_cast<const float4*>(P + (s + 3) * stride + idx);
+        acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+        acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
+        acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
+        acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+    }
+    for (; s < splits; ++s) {
+        const float4 p = *reinterpret_cast<const float4*>(P + s * stride + idx);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    return acc;
+}
+
+// x[row] = bf16(Σ partials + x[row]);  y[row] = RMSNorm(x[row]) * w      (o_proj / down_proj → next norm)
+// A thread-block cluster of RN_CLUSTER CTAs shares one row (bs=32 rows alone would occupy 32 of 148 SMs): each CTA
+// reduces d/RN_CLUSTER columns with 16-byte loads, the per-CTA sums of squares are exchanged through distributed
+// shared memory, then every CTA normalises its own columns.
+constexpr int RN_CLUSTER = 8;
+constexpr int RN_THREADS = 128;
+constexpr int RN_MAXV = 2;               // float4 groups per thread: d ≤ RN_CLUSTER · RN_THREADS · 4 · RN_MAXV = 8192
+__global__ void __cluster_dims__(RN_CLUSTER, 1, 1) __launch_bounds__(RN_THREADS)
+reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ x,
+                               const bf16* __restrict__ w, bf16* __restrict__ y, int d, float eps) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float warp_part[RN_THREADS / 32];
+    __shared__ float cta_part;
+    const int row = blockIdx.x / RN_CLUSTER;
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int cols = d / RN_CLUSTER;                 // columns owned by this CTA (multiple of 4)
+    const long long base = static_cast<long long>(row) * d + static_cast<long long>(rank) * cols;
+    float vals[RN_MAXV][4];
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < RN_MAXV; ++v) {
+        const int c = (v * RN_THREADS + threadIdx.x) * 4;
+        if (c < cols) {
+            const uint2 r = *reinterpret_cast<const uint2*>(x + base + c);
+            const float4 acc = sum_partials4(P, stride, splits, base + c);
+            // the residual stream is stored in bf16: round before the statistics, like the unfused chain
+            vals[v][0] = __bfloat162float(__float2bfloat16_rn(acc.x + bf16_lo(r.x)));
+            vals[v][1] = __bfloat162float(__float2bfloat16_rn(acc.y + bf16_hi(r.x)));
+            vals[v][2] = __bfloat162float(__float2bfloat16_rn(acc.z + bf16_lo(r.y)));
+            vals[v][3] = __bfloat162float(__float2bfloat16_rn(acc.w + bf16_hi(r.y)));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sq += vals[v][j] * vals[v][j];
+        }
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < RN_THREADS / 32; ++i) t += warp_part[i];
+        cta_part = t;
+    }
+    cluster.sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < RN_CLUSTER; ++r) tot += *cluster.map_shared_rank(&cta_part, r);     // fixed order: deterministic
+    cluster.sync();                                   // nobody leaves while its shared memory may still be read
+    const float rstd = 1.0f / sqrtf(tot / static_cast<float>(d) + eps);
+#pragma unroll
+    for (int v = 0; v < RN_MAXV; ++v) {
+        const int c = (v * RN_THREADS + threadIdx.x) * 4;
+        if (c < cols) {
+            const uint2 wv = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
+            const float wf[4] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y)};
+            *reinterpret_cast<uint2*>(x + base + c) = make_uint2(pack_bf16x2(vals[v][0], vals[v][1]), pack_bf16x2(vals[v][2], vals[v][3]));
+            *reinterpret_cast<uint2*>(y + base + c) = make_uint2(pack_bf16x2((vals[v][0] * rstd) * wf[0], (vals[v][1] * rstd) * wf[1]),
+                                                                 pack_bf16x2((vals[v][2] * rstd) * wf[2], (vals[v][3] * rstd) * wf[3]));
+        }
+    }
+}
+
+// act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i])
+__global__ void reduce_swiglu_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ act, int rows,
+                                     int inter) {
+    const int i4 = inter / 4;
+    const long long total = static_cast<long long>(rows) * i4;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / i4, c = (i % i4) * 4;
+        const float4 g = sum_partials4(P, stride, splits, r * 2 * inter + c);
+        const float4 u = sum_partials4(P, stride, splits, r * 2 * inter + inter + c);
+        const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gg = __bfloat162float(__float2bfloat16_rn(gf[j])), uu = __bfloat162float(__float2bfloat16_rn(uf[j]));
+            o[j] = (gg / (1.0f + expf(-gg))) * uu;
+        }
+        *reinterpret_cast<uint2*>(act + r * inter + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    }
+}
+
+// One warp per (sequence, head): reduce the q/k/v partials, RoPE q and k, write q into the qkv buffer and k, v
+// into the KV page of position seq_lens[seq].
+__global__ void reduce_rope_kv_write_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ qkv,
+                                            const int* __restrict__ positions, bf16* __restrict__ kv_pages,
+                                            const int* __restrict__ block_table, int max_pages, int n_seqs, int n_heads, int head_dim,
+                                            int page_size, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_seqs * n_heads) return;
+    const int seq = gw / n_heads, head = gw % n_heads;
+    const int hidden = n_heads * head_dim, half = head_dim / 2;
+    const int pos = positions[seq];
+    const int page = block_table[static_cast<size_t>(seq) * max_pages + pos / page_size];
+    const int slot = pos % page_size;
+    const long long rowbase = static_cast<long long>(seq) * 3 * hidden + head * head_dim;
+    bf16* q = qkv + rowbase;
+    bf16* kdst = kv_pages + (((static_cast<size_t>(page) * 2 + 0) * n_heads + head) * page_size + slot) * head_dim;
+    bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim;
+    const float* cs = rope_cos + static_cast<size_t>(pos) * half;
+    const float* sn = rope_sin + static_cast<size_t>(pos) * half;
+    auto r2 = [&](long long off, float& a, float& b) {          // two adjacent reduced values, rounded to bf16 like the GEMM output
+        float x0 = 0.f, x1 = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {
+            const float2 p0 = *reinterpret_cast<const float2*>(P + (sp + 0) * stride + off);
+            const float2 p1 = *reinterpret_cast<const float2*>(P + (sp + 1) * stride + off);
+            const float2 p2 = *reinterpret_cast<const float2*>(P + (sp + 2) * stride + off);
+            const float2 p3 = *reinterpret_cast<const float2*>(P + (sp + 3) * stride + off);
+            x0 += p0.x; x1 += p0.y; x0 += p1.x; x1 += p1.y; x0 += p2.x; x1 += p2.y; x0 += p3.x; x1 += p3.y;
+        }
+        for (; sp < splits; ++sp) {
+            const float2 p = *reinterpret_cast<const float2*>(P + sp * stride + off);
+            x0 += p.x; x1 += p.y;
+        }
+        a = __bfloat162float(__float2bfloat16_rn(x0));
+        b = __bfloat162float(__float2bfloat16_rn(x1));
+    };
+    for (int i = lane * 2; i < half; i += 64) {
+        const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
+        float a0, a1, b0, b1;
+        r2(rowbase + i, a0, a1);
+        r2(rowbase + i + half, b0, b1);
+        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+        r2(rowbase + hidden + i, a0, a1);
+        r2(rowbase + hidden + i + half, b0, b1);
+        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+    }
+    for (int i = lane * 4; i < head_dim; i += 128) {
+        const float4 v = sum_partials4(P, stride, splits, rowbase + 2 * hidden + i);
+        *reinterpret_cast<uint2*>(vdst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
 // ------------------------------------------------------------------------------ greedy argmax + stop rule
 // One block per sequence.  Ties → lowest index (torch.argmax semantics).  When step_ptr != NULL
 // the column is read from device memory (graph replay) and block 0 bumps it afterwards.
@@ -318,6 +495,106 @@ __global__ void argmax_step_kernel(const float* __restrict__ logits, int vocab, 
         if (seq_lens) seq_lens[seq] += 1;
     }
 }
+// Temperature / top-k sampling step (HF `sample()` with TemperatureLogitsWarper + TopKLogitsWarper, the path
+// eval/inference.py:64-72 takes with do_sample=True, temperature=0.2 and HF's default top_k=50), one block per
+// sequence:  z = logits / T;  keep z >= (k-th largest z) (ties kept, like HF's `scores < kth` mask);  softmax;
+// inverse-CDF draw in index order with u from a counter-based generator keyed by (seed, step, sequence) — so the
+// step is replayable from a CUDA graph and reproducible, but not bit-compatible with torch.multinomial's stream.
+__device__ __forceinline__ uint32_t float_order_key(float f) {          // monotone float → uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int vocab, float inv_temp, int top_k,
+                                                          unsigned long long seed, uint8_t* finished, int* tokens, int max_new,
+                                                          int step_host, const int* step_ptr, int* next_ids, int* seq_lens, int eos_id) {
+    __shared__ uint32_t hist[256];
+    __shared__ float redf[8];
+    __shared__ uint32_t sh_prefix, sh_remaining;
+    __shared__ float sh_scan[256];
+    const int seq = blockIdx.x, tid = threadIdx.x;
+    const float* row = logits + static_cast<size_t>(seq) * vocab;
+    // ---- k-th largest key by 4 radix passes (most significant byte first)
+    uint32_t prefix = 0, remaining = static_cast<uint32_t>(min(max(top_k, 1), vocab));
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t mask_hi = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int i = tid; i < vocab; i += 256) {
+            const uint32_t key = float_order_key(row[i] * inv_temp);
+            if ((key & mask_hi) == (prefix & mask_hi)) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t rem = remaining;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            sh_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+            sh_remaining = rem;
+        }
+        __syncthreads();
+        prefix = sh_prefix;
+        remaining = sh_remaining;
+    }
+    const uint32_t kth_key = prefix;        // keep keys >= kth_key
+    // ---- max and normaliser over the kept set
+    float mx = -INFINITY;
+    for (int i = tid; i < vocab; i += 256) mx = fmaxf(mx, row[i] * inv_temp);
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) redf[tid >> 5] = mx;
+    __syncthreads();
+    mx = redf[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, redf[i]);
+    __syncthreads();
+    // each thread owns a contiguous index range so the inverse-CDF walk is in index order
+    const int per = (vocab + 255) / 256, lo = tid * per, hi = min(vocab, lo + per);
+    float mine = 0.f;
+    for (int i = lo; i < hi; ++i) {
+        const float z = row[i] * inv_temp;
+        if (float_order_key(z) >= kth_key) mine += expf(z - mx);
+    }
+    sh_scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        float total = 0.f;
+        for (int i = 0; i < 256; ++i) total += sh_scan[i];
+        const int step = step_ptr ? *step_ptr : step_host;
+        const uint64_t r = splitmix64(seed + (static_cast<uint64_t>(step) * 0x100000001B3ULL + static_cast<uint64_t>(seq) + 1ULL) * 0x9E3779B97F4A7C15ULL);
+        const float u = static_cast<float>(r >> 40) * (1.0f / 16777216.0f);      // [0,1)
+        float target = u * total, acc = 0.f;
+        int owner = 255;
+        for (int i = 0; i < 256; ++i) {
+            if (acc + sh_scan[i] > target) { owner = i; break; }
+            acc += sh_scan[i];
+        }
+        // walk the owner's range
+        int pick = -1;
+        const int olo = owner * per, ohi = min(vocab, olo + per);
+        for (int i = olo; i < ohi; ++i) {
+            const float z = row[i] * inv_temp;
+            if (float_order_key(z) >= kth_key) {
+                pick = i;                                   // last kept index is the fallback for rounding at the tail
+                acc += expf(z - mx);
+                if (acc > target) break;
+            }
+        }
+        if (pick < 0) {                                     // numerical corner: fall back to the arg-max
+            float best = -INFINITY;
+            for (int i = 0; i < vocab; ++i) if (row[i] > best) { best = row[i]; pick = i; }
+        }
+        const bool was_done = finished[seq] != 0;
+        const int tok = was_done ? eos_id : pick;
+        if (step < max_new) tokens[static_cast<size_t>(seq) * max_new + step] = was_done ? -1 : tok;
+        if (!was_done && tok == eos_id) finished[seq] = 1;
+        next_ids[seq] = tok;
+        if (seq_lens) seq_lens[seq] += 1;
+    }
+}
+
 __global__ void bump_step_kernel(int* step_ptr) { *step_ptr += 1; }
 
 }  // namespace teo
@@ -433,11 +710,53 @@ int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, vo
     TEO_LAUNCH_CHECK("rope_kv_write_kernel");
     return TEO_OK;
 }
+int launch_reduce_residual_rmsnorm(const float* P, long long stride, int splits, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps,
+                                   cudaStream_t stream) {
+    TEO_CHECK_ARG(P && x && w && y && rows > 0 && splits >= 1, "reduce_residual_rmsnorm: bad arguments");
+    TEO_CHECK_ARG(d > 0 && d % (RN_CLUSTER * 4) == 0 && d <= RN_CLUSTER * RN_THREADS * 4 * RN_MAXV,
+                  "reduce_residual_rmsnorm: d=%d must be a multiple of %d and <= %d", d, RN_CLUSTER * 4, RN_CLUSTER * RN_THREADS * 4 * RN_MAXV);
+    reduce_residual_rmsnorm_kernel<<<rows * RN_CLUSTER, RN_THREADS, 0, stream>>>(P, stride, splits, x, w, y, d, eps);
+    TEO_LAUNCH_CHECK("reduce_residual_rmsnorm_kernel");
+    return TEO_OK;
+}
+int launch_reduce_swiglu(const float* P, long long stride, int splits, bf16* act, int rows, int inter, cudaStream_t stream) {
+    TEO_CHECK_ARG(P && act && rows > 0 && inter > 0 && splits >= 1, "reduce_swiglu: bad arguments");
+    TEO_CHECK_ARG(inter % 4 == 0, "reduce_swiglu: inter %% 4 != 0");
+    const long long total = static_cast<long long>(rows) * (inter / 4);
+    reduce_swiglu_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(P, stride, splits, act, rows, inter);
+    TEO_LAUNCH_CHECK("reduce_swiglu_kernel");
+    return TEO_OK;
+}
+int launch_reduce_rope_kv_write(const float* P, long long stride, int splits, void* qkv, const int* positions, void* kv_pages,
+                                const int* block_table, int max_pages, int n_seqs, int n_heads, int head_dim, int page_size,
+                                const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
+    TEO_CHECK_ARG(P && qkv && positions && kv_pages && block_table && rope_cos && rope_sin && splits >= 1, "reduce_rope_kv_write: null pointer");
+    const long long warps = static_cast<long long>(n_seqs) * n_heads;
+    reduce_rope_kv_write_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        P, stride, splits, static_cast<bf16*>(qkv), positions, static_cast<bf16*>(kv_pages), block_table, max_pages, n_seqs, n_heads, head_dim,
+        page_size, rope_cos, rope_sin);
+    TEO_LAUNCH_CHECK("reduce_rope_kv_write_kernel");
+    return TEO_OK;
+}
+int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
+                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream) {
+    TEO_CHECK_ARG(logits && finished && tokens && next_ids, "sample_step: null pointer");
+    TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0 && temperature > 0.f, "sample_step: bad sizes / temperature");
+    if (top_k <= 0 || top_k > vocab) top_k = vocab;
+    sample_step_kernel<<<n_seqs, 256, 0, stream>>>(logits, vocab, 1.0f / temperature, top_k, seed, finished, tokens, max_new, step_host, step_ptr,
+                                                   next_ids, seq_lens, eos_id);
+    TEO_LAUNCH_CHECK("sample_step_kernel");
+    if (step_ptr) {
+        bump_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+        TEO_LAUNCH_CHECK("bump_step_kernel");
+    }
+    return TEO_OK;
+}
 int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
                        int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream) {
     TEO_CHECK_ARG(logits && finished && tokens && next_ids, "argmax_step: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0, "argmax_step: bad sizes");
-    argmax_step_kernel<<<n_seqs, 256, 0, stream>>>(logits, vocab, finished, tokens, max_new, step_host, step_ptr, next_ids, seq_lens, eos_id);
+    argmax_step_kernel<<<n_seqs, 1024, 0, stream>>>(logits, vocab, finished, tokens, max_new, step_host, step_ptr, next_ids, seq_lens, eos_id);
     TEO_LAUNCH_CHECK("argmax_step_kernel");
     if (step_ptr) {
         bump_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
@@ -453,6 +772,12 @@ extern "C" int teo_rope_kv_write(void* qkv, const void* positions, const void* s
     return launch_rope_kv_write(qkv, static_cast<const int*>(positions), static_cast<const int*>(seq_ids), kv_pages,
                                 static_cast<const int*>(block_table), max_pages, tokens, n_heads, head_dim, page_size,
                                 static_cast<const float*>(rope_cos), static_cast<const float*>(rope_sin), static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_sample_step(const void* logits, int vocab, float temperature, int top_k, uint64_t seed, void* finished, void* tokens,
+                               int max_new, int step, void* next_ids, int n_seqs, int eos_id, void* stream) {
+    return launch_sample_step(static_cast<const float*>(logits), vocab, temperature, top_k, seed, static_cast<uint8_t*>(finished),
+                              static_cast<int*>(tokens), max_new, step, nullptr, static_cast<int*>(next_ids), nullptr, n_seqs, eos_id,
+                              static_cast<cudaStream_t>(stream));
 }
 extern "C" int teo_argmax_step(const void* logits, int vocab, void* finished, void* tokens, int max_new, int step, void* next_ids,
                                int n_seqs, int eos_id, void* stream) {

@@ -32,6 +32,15 @@ int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, vo
 int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
                        int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
 
+int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
+                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
+int launch_reduce_residual_rmsnorm(const float* P, long long stride, int splits, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps,
+                                   cudaStream_t stream);
+int launch_reduce_swiglu(const float* P, long long stride, int splits, bf16* act, int rows, int inter, cudaStream_t stream);
+int launch_reduce_rope_kv_write(const float* P, long long stride, int splits, void* qkv, const int* positions, void* kv_pages,
+                                const int* block_table, int max_pages, int n_seqs, int n_heads, int head_dim, int page_size,
+                                const float* rope_cos, const float* rope_sin, cudaStream_t stream);
+
 __global__ void fill_cu_seqlens_kernel(int* cu, int n, int len) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) cu[i] = i * len;
@@ -88,6 +97,13 @@ extern "C" int teo_create(int device_id, teo_handle** out) {
 }
 extern "C" int teo_destroy(teo_handle* h) {
     delete h;
+    return TEO_OK;
+}
+extern "C" int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed) {
+    TEO_CHECK_ARG(h != nullptr, "teo_set_sampling: null handle");
+    h->temperature = temperature;
+    h->top_k = top_k;
+    h->sample_seed = seed;
     return TEO_OK;
 }
 extern "C" unsigned long long teo_launch_count(const teo_handle* h) { return h ? h->launches : 0ULL; }
@@ -349,37 +365,75 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
         return TEO_ERR_WORKSPACE;
     }
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    const int I = m->inter;
+    const bool fused = n_seqs <= 128 && hdim >= 256 && hdim % 32 == 0 && hdim <= 8192 && I % 4 == 0;   // swap-AB split-K regime of the GEMM
     TEO_TRY(teo_splice_embed(m->embed, nullptr, next_ids, w.x, n_seqs, hdim, stream));
-    h->launches += 1;
+    TEO_TRY(teo_rmsnorm(w.x, m->layer[0].in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
+    h->launches += 2;
+    const float* P = reinterpret_cast<const float*>(w.gemm_ws);
     for (int l = 0; l < m->layers; ++l) {
         const teo_llama_layer& L = m->layer[l];
-        TEO_TRY(teo_rmsnorm(w.x, L.in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
-        GemmEpilogue none;
-        TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, n_seqs, 3 * hdim, hdim, none,
-                            w.gemm_ws, w.gemm_ws_bytes, stream));
-        // position of the new token = tokens cached so far
-        TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(seq_lens), nullptr, L.kv_pages, static_cast<const int*>(block_table),
-                                     max_pages, n_seqs, m->heads, hd, m->page_size, static_cast<const float*>(m->rope_cos),
-                                     static_cast<const float*>(m->rope_sin), stream));
-        TEO_TRY(launch_decode_attention(h, w.qkv, 3 * hdim, static_cast<const bf16*>(L.kv_pages), static_cast<const int*>(block_table),
-                                        max_pages, static_cast<const int*>(seq_lens), 1, w.attn, n_seqs, m->heads, hd, m->page_size,
-                                        max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
-        GemmEpilogue res;
-        res.residual = w.x;
-        res.ldr = hdim;
-        TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, w.x, hdim, n_seqs, hdim, hdim, res, w.gemm_ws,
-                            w.gemm_ws_bytes, stream));
-        h->launches += 2;
-        TEO_TRY(llama_layer_mlp(h, m, L, w.x, n_seqs, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
+        const void* next_norm = (l + 1 < m->layers) ? m->layer[l + 1].in_norm : m->final_norm;
+        if (fused) {
+            int sp = 1;
+            // qkv: GEMM partials → reduce + RoPE + KV-page write (position of the new token = tokens cached so far)
+            TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, n_seqs, 3 * hdim, hdim, w.gemm_ws,
+                                         w.gemm_ws_bytes, &sp, stream));
+            TEO_TRY(launch_reduce_rope_kv_write(P, static_cast<long long>(n_seqs) * 3 * hdim, sp, w.qkv, static_cast<const int*>(seq_lens),
+                                                L.kv_pages, static_cast<const int*>(block_table), max_pages, n_seqs, m->heads, hd,
+                                                m->page_size, static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin),
+                                                stream));
+            TEO_TRY(launch_decode_attention(h, w.qkv, 3 * hdim, static_cast<const bf16*>(L.kv_pages), static_cast<const int*>(block_table),
+                                            max_pages, static_cast<const int*>(seq_lens), 1, w.attn, n_seqs, m->heads, hd, m->page_size,
+                                            max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
+            // o_proj partials → reduce + residual + post-attention RMSNorm
+            TEO_TRY(launch_gemm_partials(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, n_seqs, hdim, hdim, w.gemm_ws, w.gemm_ws_bytes,
+                                         &sp, stream));
+            TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(L.post_norm),
+                                                   w.norm_out, n_seqs, hdim, m->eps, stream));
+            // gate/up partials → reduce + SwiGLU
+            TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
+                                         w.gemm_ws_bytes, &sp, stream));
+            TEO_TRY(launch_reduce_swiglu(P, static_cast<long long>(n_seqs) * 2 * I, sp, w.act, n_seqs, I, stream));
+            // down_proj partials → reduce + residual + the NEXT layer's input RMSNorm (or the final norm)
+            TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &sp,
+                                         stream));
+            TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(next_norm),
+                                                   w.norm_out, n_seqs, hdim, m->eps, stream));
+            h->launches += 4;
+        } else {
+            GemmEpilogue none;
+            TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, n_seqs, 3 * hdim, hdim, none,
+                                w.gemm_ws, w.gemm_ws_bytes, stream));
+            TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(seq_lens), nullptr, L.kv_pages, static_cast<const int*>(block_table),
+                                         max_pages, n_seqs, m->heads, hd, m->page_size, static_cast<const float*>(m->rope_cos),
+                                         static_cast<const float*>(m->rope_sin), stream));
+            TEO_TRY(launch_decode_attention(h, w.qkv, 3 * hdim, static_cast<const bf16*>(L.kv_pages), static_cast<const int*>(block_table),
+                                            max_pages, static_cast<const int*>(seq_lens), 1, w.attn, n_seqs, m->heads, hd, m->page_size,
+                                            max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
+            GemmEpilogue res;
+            res.residual = w.x;
+            res.ldr = hdim;
+            TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, w.x, hdim, n_seqs, hdim, hdim, res, w.gemm_ws,
+                                w.gemm_ws_bytes, stream));
+            h->launches += 1;
+            TEO_TRY(llama_layer_mlp(h, m, L, w.x, n_seqs, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
+            TEO_TRY(teo_rmsnorm(w.x, next_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
+            h->launches += 1;
+        }
     }
-    TEO_TRY(teo_rmsnorm(w.x, m->final_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
     GemmEpilogue lg;
     lg.out_fp32 = 1;
     TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(m->lm_head), hdim, logits, m->vocab, n_seqs, m->vocab, hdim, lg,
                         w.gemm_ws, w.gemm_ws_bytes, stream));
-    TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
-                               max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,
-                               eos_id, stream));
+    if (h->temperature > 0.f)
+        TEO_TRY(launch_sample_step(static_cast<const float*>(logits), m->vocab, h->temperature, h->top_k, h->sample_seed,
+                                   static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new, 0, static_cast<int*>(step_ptr),
+                                   static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream));
+    else
+        TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
+                                   max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,
+                                   eos_id, stream));
     h->launches += 3;
     return TEO_OK;
 }

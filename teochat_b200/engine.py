@@ -206,12 +206,15 @@ class TeoModel:
     @torch.no_grad()
     def generate_batch(self, input_ids: Sequence[Sequence[int]], frames_u8: Optional[Sequence[torch.Tensor]] = None,
                        pixel_values: Optional[Sequence[torch.Tensor]] = None, max_new_tokens: int = 256,
-                       eos_token_id: Optional[int] = None, return_logits: bool = False, time_phases: bool = False):
+                       eos_token_id: Optional[int] = None, return_logits: bool = False, time_phases: bool = False,
+                       temperature: float = 0.0, top_k: int = 50, seed: int = 0):
         """Greedy generation for a ragged batch of independent (image sequence, prompt) pairs.
 
         frames_u8[i]: u8 [T_i,H,W,3] (host or device) — or pixel_values[i]: f32 [T_i,3,H,W].
         Returns a list of per-sample new-token id lists (eos included if produced), like
         ``output_ids[0, input_ids.shape[1]:]`` in eval/inference.py:75.
+        ``temperature > 0`` samples on the device (temperature + top-k + multinomial, the reference's default
+        decode mode, inference.py:67-69; HF's default top_k=50); ``temperature <= 0`` is greedy.
         """
         cfg, l = self.cfg, self.cfg.llama
         B = len(input_ids)
@@ -220,6 +223,9 @@ class TeoModel:
         if max_new_tokens < 1:
             raise ValueError("max_new_tokens must be >= 1")
         eos = l.eos_token_id if eos_token_id is None else eos_token_id
+        sampling = temperature is not None and temperature > 0
+        L.check(self.lib.teo_set_sampling(self._h, float(temperature) if sampling else 0.0, int(top_k), C.c_uint64(seed & (2 ** 64 - 1))),
+                "teo_set_sampling")
         imgs = frames_u8 if frames_u8 is not None else pixel_values
         if imgs is None or len(imgs) != B:
             raise ValueError("need one image stack per sample")
@@ -287,8 +293,13 @@ class TeoModel:
         tokens = torch.full((B, max_new_tokens), -1, dtype=torch.int32, device=dev)
         next_ids = torch.empty(B, dtype=torch.int32, device=dev)
         step_ptr = torch.ones(1, dtype=torch.int32, device=dev)
-        L.check(self.lib.teo_argmax_step(logits.data_ptr(), l.vocab_size, finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0,
-                                         next_ids.data_ptr(), B, eos, stream), "teo_argmax_step")
+        if sampling:
+            L.check(self.lib.teo_sample_step(logits.data_ptr(), l.vocab_size, float(temperature), int(top_k), C.c_uint64(seed & (2 ** 64 - 1)),
+                                             finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0, next_ids.data_ptr(), B, eos, stream),
+                    "teo_sample_step")
+        else:
+            L.check(self.lib.teo_argmax_step(logits.data_ptr(), l.vocab_size, finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0,
+                                             next_ids.data_ptr(), B, eos, stream), "teo_argmax_step")
         step_logits = [logits.clone()] if return_logits else None
         if ev:
             ev[2].record()
@@ -356,8 +367,7 @@ class TeoModel:
         SURVEY.md §8 quirk 6)."""
         if input_ids is None or input_ids.dim() != 2 or input_ids.shape[0] != 1:
             raise ValueError("generate expects input_ids of shape [1, L]; use generate_batch for batches")
-        if do_sample and temperature and temperature > 0:
-            raise NotImplementedError("sampling (temperature>0) is SURVEY.md §8(f) row 3; pass temperature=0 for the greedy parity path")
+        sample_t = float(temperature) if (do_sample and temperature and temperature > 0) else 0.0
         eos = self.cfg.llama.eos_token_id
         if stopping_criteria:
             for sc in stopping_criteria:
@@ -372,6 +382,7 @@ class TeoModel:
         if px.dim() == 3:
             px = px[None]
         ids = input_ids[0].tolist()
-        out = self.generate_batch([ids], pixel_values=[px], max_new_tokens=max_new_tokens)[0]
+        out = self.generate_batch([ids], pixel_values=[px], max_new_tokens=max_new_tokens, temperature=sample_t,
+                                  top_k=int(kwargs.get("top_k", 50) or 0), seed=int(kwargs.get("seed", 0)))[0]
         new = torch.tensor(out, dtype=input_ids.dtype, device=input_ids.device)[None]
         return torch.cat([input_ids, new], dim=1)

@@ -49,7 +49,8 @@ def build_prompt(inp: str, image_paths, conv_mode="v1", timestamps=(), prompt_st
 def run_inference_single(model, processor, tokenizer, inp, image_paths, conv_mode="v1", timestamps=[],
                          prompt_strategy="interleave", chronological_prefix=True, temperature=0.2,
                          max_new_tokens=256):
-    """inference.py:23-77.  ``temperature <= 0`` selects greedy decoding (the parity path)."""
+    """inference.py:23-77.  ``temperature > 0`` samples on the device (reference default 0.2);
+    ``temperature <= 0`` selects greedy decoding (the parity path)."""
     prompt, image_paths, stop_str = build_prompt(inp, image_paths, conv_mode, timestamps, prompt_strategy,
                                                  chronological_prefix)
     tensors = [processor.preprocess(i, return_tensors="pt")["pixel_values"][0] for i in image_paths]
@@ -66,11 +67,9 @@ def run_inference_single(model, processor, tokenizer, inp, image_paths, conv_mod
 def run_inference_batch(model, processor, tokenizer, inps: Sequence[str], image_paths_list: Sequence[Sequence],
                         conv_mode="v1", timestamps_list: Optional[Sequence[Sequence[str]]] = None,
                         prompt_strategy="interleave", chronological_prefix=True, temperature=0.0,
-                        max_new_tokens=256) -> List[str]:
+                        max_new_tokens=256, seed: int = 0) -> List[str]:
     """Batched greedy form of run_inference_single: one ViT pass over all frames, one ragged
     prefill, one graph-replayed decode loop.  Result i equals run_inference_single on example i."""
-    if temperature and temperature > 0:
-        raise NotImplementedError("batched path is greedy (temperature=0)")
     ids_list, frames = [], []
     raw = hasattr(processor, "to_uint8_nhwc")
     for n, (inp, paths) in enumerate(zip(inps, image_paths_list)):
@@ -78,7 +77,8 @@ def run_inference_batch(model, processor, tokenizer, inps: Sequence[str], image_
         prompt, paths, _ = build_prompt(inp, paths, conv_mode, ts, prompt_strategy, chronological_prefix)
         ids_list.append(tokenizer_image_token(prompt, tokenizer, IMAGE_TOKEN_INDEX))
         frames.append(torch.cat([processor.preprocess(p, return_tensors="pt")["pixel_values"] for p in paths]))
-    outs = model.generate_batch(ids_list, pixel_values=frames, max_new_tokens=max_new_tokens)
+    outs = model.generate_batch(ids_list, pixel_values=frames, max_new_tokens=max_new_tokens,
+                                temperature=temperature or 0.0, seed=seed)
     return [tokenizer.decode(o).replace("</s>", "").strip() for o in outs]
 
 
@@ -94,7 +94,7 @@ def run_inference(dataset, model, tokenizer, processor, prompt_strategy, chronol
     run_inference_batch."""
     examples = list(dataset)
     responses: List[str] = []
-    if batch_size > 1 and not (temperature and temperature > 0):
+    if batch_size > 1:
         for s in range(0, len(examples), batch_size):
             chunk = examples[s:s + batch_size]
             responses += run_inference_batch(model, processor, tokenizer,
@@ -102,8 +102,8 @@ def run_inference(dataset, model, tokenizer, processor, prompt_strategy, chronol
                                              [e["video"] for e in chunk], conv_mode=conv_mode,
                                              timestamps_list=[e["timestamp"] for e in chunk],
                                              prompt_strategy=prompt_strategy,
-                                             chronological_prefix=chronological_prefix, temperature=0.0,
-                                             max_new_tokens=max_new_tokens)
+                                             chronological_prefix=chronological_prefix, temperature=temperature,
+                                             max_new_tokens=max_new_tokens, seed=s)
     else:
         for e in examples:
             responses.append(run_inference_single(model, processor, tokenizer, e["conversations"][0]["value"], e["video"],

@@ -75,6 +75,8 @@ _SIGS = {
     "teo_swiglu": (i, [vp, vp, i, i, vp]),
     "teo_splice_embed": (i, [vp, vp, vp, vp, i, i, vp]),
     "teo_argmax_step": (i, [vp, i, vp, vp, i, i, vp, i, i, vp]),
+    "teo_sample_step": (i, [vp, i, f, i, u64, vp, vp, i, i, vp, i, i, vp]),
+    "teo_set_sampling": (i, [vp, f, i, u64]),
     "teo_vit_workspace_bytes": (sz, [C.POINTER(VitModel), i]),
     "teo_vit_encode": (i, [vp, C.POINTER(VitModel), vp, vp, i, vp, vp, sz, vp]),
     "teo_projector_workspace_bytes": (sz, [C.POINTER(Projector), i]),

@@ -230,6 +230,13 @@ def test_reference_api_drop_in(tmp_path):
     assert b == [a]
     with pytest.raises(ValueError):
         run_inference_single(model, processor, tokenizer, inp, paths, prompt_strategy="bogus", temperature=0)
+    # the reference's default decode mode (do_sample=True, temperature=0.2) runs on the device
+    c = run_inference_single(model, processor, tokenizer, inp, paths, max_new_tokens=8)
+    assert isinstance(c, str)
+    d1 = model.generate_batch([[1, -200, 5]], pixel_values=[torch.zeros(1, 3, 56, 56)], max_new_tokens=12, temperature=1.5, seed=7)
+    d2 = model.generate_batch([[1, -200, 5]], pixel_values=[torch.zeros(1, 3, 56, 56)], max_new_tokens=12, temperature=1.5, seed=7)
+    d3 = model.generate_batch([[1, -200, 5]], pixel_values=[torch.zeros(1, 3, 56, 56)], max_new_tokens=12, temperature=1.5, seed=8)
+    assert d1 == d2 and d1 != d3            # graph-replayed sampling is reproducible per seed
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "config1_full.npz")), reason="full-size fixture not generated")

@@ -286,3 +286,48 @@ def test_decode_attention(teo, hd, ps, H, lens):
         ref = (torch.einsum("hqk,khd->qhd", p.to(torch.bfloat16).float(), V) / p.sum(-1).transpose(0, 1)[..., None]).reshape(-1)
         err = (out[b].float() - ref).abs().max().item()
         assert err <= 1.5e-2 * ref.abs().max().item(), (b, n, err)
+
+
+def test_sample_step_distribution(teo):
+    """Temperature + top-k sampling: only top-k ids are drawn, frequencies follow softmax(z/T) restricted to the
+    top-k set, draws are reproducible per (seed, step, sequence) and T→0 degenerates to arg-max."""
+    lib, _ = teo
+    V, B, max_new, T, K = 1000, 8192, 4, 0.7, 5
+    base = rnd(V, seed=5)
+    lg = base[None].repeat(B, 1).contiguous()
+    fin = torch.zeros(B, dtype=torch.uint8, device=DEV)
+    toks = torch.full((B, max_new), -1, dtype=torch.int32, device=DEV)
+    nxt = torch.empty(B, dtype=torch.int32, device=DEV)
+    L.check(lib.teo_sample_step(lg.data_ptr(), V, T, K, C.c_uint64(123), fin.data_ptr(), toks.data_ptr(), max_new, 1, nxt.data_ptr(), B, 2,
+                                stream()))
+    draws = toks[:, 1].long()
+    topv, topi = (base / T).topk(K)
+    assert set(draws.tolist()) <= set(topi.tolist())
+    want = torch.softmax(topv, 0)
+    freq = torch.stack([(draws == i).float().mean() for i in topi])
+    assert (freq - want).abs().max().item() < 0.02                  # 8192 draws: 3 sigma ≈ 0.017
+    toks2 = torch.full((B, max_new), -1, dtype=torch.int32, device=DEV)
+    fin.zero_()
+    L.check(lib.teo_sample_step(lg.data_ptr(), V, T, K, C.c_uint64(123), fin.data_ptr(), toks2.data_ptr(), max_new, 1, nxt.data_ptr(), B, 2,
+                                stream()))
+    assert torch.equal(toks[:, 1], toks2[:, 1])                     # same (seed, step, seq) → same draw
+    fin.zero_()
+    L.check(lib.teo_sample_step(lg.data_ptr(), V, T, K, C.c_uint64(124), fin.data_ptr(), toks2.data_ptr(), max_new, 1, nxt.data_ptr(), B, 2,
+                                stream()))
+    assert not torch.equal(toks[:, 1], toks2[:, 1])
+    fin.zero_()
+    L.check(lib.teo_sample_step(lg.data_ptr(), V, 1e-4, 50, C.c_uint64(1), fin.data_ptr(), toks2.data_ptr(), max_new, 2, nxt.data_ptr(), B, 2,
+                                stream()))
+    assert (toks2[:, 2] == int(base.argmax())).all()
+    # ties at the k-th value are all kept (HF masks scores < kth)
+    tie = torch.full((4, 64), -5.0, device=DEV)
+    tie[:, 10] = 1.0; tie[:, 20] = 0.5; tie[:, 30] = 0.5
+    fin4 = torch.zeros(4, dtype=torch.uint8, device=DEV)
+    t4 = torch.full((4, 2), -1, dtype=torch.int32, device=DEV)
+    n4 = torch.empty(4, dtype=torch.int32, device=DEV)
+    seen = set()
+    for sd in range(40):
+        fin4.zero_()
+        L.check(lib.teo_sample_step(tie.data_ptr(), 64, 1.0, 2, C.c_uint64(sd), fin4.data_ptr(), t4.data_ptr(), 2, 0, n4.data_ptr(), 4, 2, stream()))
+        seen |= set(t4[:, 0].tolist())
+    assert seen == {10, 20, 30}
