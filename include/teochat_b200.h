@@ -67,6 +67,16 @@ int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* W, int ldw,
                   int K, const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Blocked weight layout.  A weight matrix W[N,K] (N % 128 == 0, K % 64 == 0) may be stored as
+ * bf16 [N/128][K/64][128][64]: each 128-row × 64-column operand tile is 16 KiB CONTIGUOUS in HBM, so the TMA
+ * producer streams whole DRAM bursts instead of 128 separate 128-byte row pieces 2·K bytes apart (what bounds the
+ * weight-streaming decode GEMMs).  teo_weight_to_blocked converts out of place; teo_gemm_bf16_wblocked is
+ * teo_gemm_bf16 for such a W (same results). */
+int teo_weight_to_blocked(const void* w_rowmajor, void* w_blocked, int N, int K, void* stream);
+int teo_gemm_bf16_wblocked(teo_handle* h, const void* A, int lda, const void* W_blocked, void* C, int ldc, int M, int N,
+                           int K, const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- vision tower pieces --------------------------------------------------------------- */
 /* ToTensor+Normalize (processing_image.py:18,22) fused with im2col for the 14x14/14 patch conv
  * (HF CLIPVisionEmbeddings.patch_embedding): frames u8 [n,H,W,3] NHWC → patches bf16 [n*g*g, kpad],
@@ -141,6 +151,10 @@ int teo_sample_step(const void* logits, int vocab, float temperature, int top_k,
 /* select how teo_llama_decode_step picks the next token for this handle: temperature <= 0 → greedy */
 int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed);
 
+/* programmatic dependent launch between the kernels of teo_llama_decode_step (default on): each kernel's launch,
+ * prologue and — for the GEMMs — weight prefetch overlap the tail of its predecessor.  Results are identical. */
+int teo_set_pdl(teo_handle* h, int enabled);
+
 /* ---- whole-model entry points ---------------------------------------------------------- */
 typedef struct {
     const void *ln1_w, *ln1_b;   /* [d] */
@@ -154,6 +168,7 @@ typedef struct {
 typedef struct {
     int hidden, inter, heads, image, patch, kpad, act, layers_run;
     float eps;
+    int w_blocked;               /* != 0: every GEMM weight below is in the blocked layout (teo_weight_to_blocked) */
     const void* patch_w;         /* [hidden, kpad] bf16, columns (c*P+ky)*P+kx, zero padded */
     const void *cls, *pos;       /* [hidden], [np+1, hidden] */
     const void *pre_ln_w, *pre_ln_b;
@@ -170,6 +185,7 @@ int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void* frames_u8,
 
 typedef struct {
     int in_dim, hidden;
+    int w_blocked;       /* != 0: w0 / w2 in the blocked layout */
     const void *w0, *b0; /* [hidden, in_dim], [hidden] */
     const void *w2, *b2; /* [hidden, hidden], [hidden] */
 } teo_projector;
@@ -191,6 +207,7 @@ typedef struct {
 typedef struct {
     int hidden, inter, heads, layers, vocab, page_size, rope_max_pos;
     float eps;
+    int w_blocked;                   /* != 0: qkv_w / o_w / gate_up_w / down_w / lm_head in the blocked layout (embed stays row-major) */
     const void *rope_cos, *rope_sin; /* f32 [rope_max_pos, head_dim/2] */
     const void* embed;      /* [vocab, h] */
     const void* final_norm; /* [h] */

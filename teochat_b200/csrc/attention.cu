@@ -255,6 +255,8 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
 
     const int split = blockIdx.x, n_splits = gridDim.x, head = blockIdx.y, seq = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31;
+    pdl_trigger();
+    pdl_wait();                                  // q, the new K/V rows and seq_lens come from the previous kernels
     const int len = seq_lens[seq] + len_bias;
     const int n_pages = (len + PAGE - 1) / PAGE;
     const int pps = (n_pages + n_splits - 1) / n_splits;
@@ -364,6 +366,8 @@ __global__ void decode_combine_kernel(const float* __restrict__ o_part, const fl
                                       int n_heads, int n_splits, float scale_log2) {
     const int head = blockIdx.x, seq = blockIdx.y;
     const long long base = static_cast<long long>(seq) * n_heads + head;
+    pdl_trigger();
+    pdl_wait();
     float M = -INFINITY;
     for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ml_part[(base * n_splits + s) * 2]);
     float L = 0.f;
@@ -414,11 +418,12 @@ static int launch_decode_t(const bf16* q, int ldq, const bf16* kv_pages, const i
     }
     const float sl2 = scale * 1.4426950408889634f;
     dim3 grid(splits, n_heads, n_seqs);
-    decode_attn_kernel<HD, PAGE><<<grid, DEC_THREADS, SMEM, stream>>>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out,
-                                                                      o_part, ml_part, n_heads, sl2);
+    TEO_CUDA(launch_kc(PDL_ATTN, decode_attn_kernel<HD, PAGE>, grid, dim3(DEC_THREADS), SMEM, stream, q, static_cast<long long>(ldq), kv_pages, block_table,
+                      max_pages, seq_lens, len_bias, out, o_part, ml_part, n_heads, sl2));
     TEO_LAUNCH_CHECK("decode_attn_kernel");
     if (splits > 1) {
-        decode_combine_kernel<HD><<<dim3(n_heads, n_seqs), HD, 0, stream>>>(o_part, ml_part, out, n_heads, splits, sl2);
+        TEO_CUDA(launch_k(decode_combine_kernel<HD>, dim3(n_heads, n_seqs), dim3(HD), 0, stream, static_cast<const float*>(o_part),
+                          static_cast<const float*>(ml_part), out, n_heads, splits, sl2));
         TEO_LAUNCH_CHECK("decode_combine_kernel");
     }
     return TEO_OK;

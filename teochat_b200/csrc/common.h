@@ -17,6 +17,35 @@ typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
 
+// Programmatic dependent launch (PDL) switch for the launch helpers below: while it is on (decode step), kernels
+// are launched with cudaLaunchAttributeProgrammaticStreamSerialization so that a kernel's launch, prologue and
+// (for the GEMM) weight prefetch overlap the tail of its predecessor; every kernel calls griddepcontrol.wait
+// before touching data its predecessor produced.
+bool pdl_enabled();
+void set_pdl(bool on);
+// which kernel classes get the attribute (bit 0 GEMM, bit 1 attention, bit 2 small glue kernels); TEO_PDL_MASK env
+int pdl_mask();
+constexpr int PDL_GEMM = 1, PDL_ATTN = 2, PDL_SMALL = 4;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kc(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_enabled() && (pdl_mask() & kind)) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_kc(PDL_SMALL, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+
 #define TEO_CHECK_ARG(cond, ...)            \
     do {                                    \
         if (!(cond)) {                      \
@@ -78,6 +107,7 @@ struct teo_handle {
     float temperature = 0.f;           // > 0 → teo_llama_decode_step samples (teo_set_sampling)
     int top_k = 50;
     unsigned long long sample_seed = 0;
+    bool pdl = true;                   // programmatic dependent launch inside teo_llama_decode_step (teo_set_pdl)
     std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
 };
 
@@ -99,10 +129,10 @@ struct GemmEpilogue {
 // C[M,N] = epilogue(A[M,K] · W[N,K]^T).  Chooses the swap-AB / split-K schedule for small M.
 // workspace: teo_gemm_workspace_bytes(M,N,K) bytes (only used by the split-K schedule).
 int launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
-                const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream, int w_blocked = 0);
 
 // Small-M (decode) GEMM that stops at fp32 split-K partials P[s][M][N]; the consumer kernel reduces them.
 int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                         size_t workspace_bytes, int* splits_out, cudaStream_t stream);
+                         size_t workspace_bytes, int* splits_out, cudaStream_t stream, int w_blocked = 0);
 
 }  // namespace teo

@@ -58,6 +58,8 @@ struct GemmArgs {
     int kb_per_split;           // K blocks per split
     int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
     int force_partial;          // write fp32 partials even when splits == 1
+    int w_is_a;                 // operand A holds the (constant) weights: may be fetched before griddepcontrol.wait
+    int w_blocked;              // weights stored tile-blocked [N/128][K/64][128][64] (4-D tensor map)
 };
 
 template <int BN>
@@ -106,6 +108,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* res_bar = tempty_bar + 2;                                 // [EPI_WARPS] residual tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
+    pdl_trigger();                               // let the next kernel's launch + prologue overlap this one
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_m = (g.M + BM - 1) / BM;
@@ -144,16 +147,51 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            // operand loads: weights may live in the blocked layout (contiguous 16 KiB tiles → full-rate HBM bursts)
+            auto load_a = [&](int st, int kb, int m_blk) {
+                if (g.w_is_a && g.w_blocked) tma_load_4d(smem_a + st * A_STAGE_BYTES, &tma_a, &full_bar[st], 0, 0, kb, m_blk);
+                else tma_load_2d(smem_a + st * A_STAGE_BYTES, &tma_a, &full_bar[st], kb * BK, m_blk * BM);
+            };
+            auto load_b = [&](int st, int kb, int n_blk) {
+                if (!g.w_is_a && g.w_blocked) tma_load_4d(smem_b + st * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[st], 0, 0, kb, n_blk * (BN / 128));
+                else tma_load_2d(smem_b + st * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[st], kb * BK, n_blk * BN);
+            };
+            // Under programmatic dependent launch the activations are produced by the previous kernel but the
+            // weights are constant: fill the ring with weight tiles first, wait for the dependency, then add
+            // the activation tiles of those stages (each full barrier expects both).
+            int pre = 0;
+            {
+                int cnt = 0;
+                for (int unit = blockIdx.x; unit < num_units && cnt < STAGES; unit += gridDim.x) {
+                    int m_blk, n_blk, split;
+                    unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
+                    const int kb0 = split * g.kb_per_split;
+                    const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+                    for (int kb = kb0; kb < kb1 && cnt < STAGES; ++kb, ++cnt) {
+                        mbar_arrive_expect_tx(&full_bar[cnt], Cfg::STAGE_BYTES);
+                        if (g.w_is_a) load_a(cnt, kb, m_blk);
+                        else load_b(cnt, kb, n_blk);
+                    }
+                }
+                pre = cnt;
+            }
+            pdl_wait();
+            int done = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 int m_blk, n_blk, split;
                 unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(total_kb, kb0 + g.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                    tma_load_2d(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
-                    tma_load_2d(smem_b + s * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[s], kb * BK, n_blk * BN);
+                for (int kb = kb0; kb < kb1; ++kb, ++done) {
+                    if (done < pre) {               // weights already in flight: add the other operand
+                        if (g.w_is_a) load_b(s, kb, n_blk);
+                        else load_a(s, kb, m_blk);
+                    } else {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        load_a(s, kb, m_blk);
+                        load_b(s, kb, n_blk);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -195,6 +233,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
+        pdl_wait();                              // outputs / residual / partial workspace belong to the previous kernel until now
         const int ew = warp - 4;                 // 0..7
         const int q = ew & 3;                    // TMEM lane quadrant this warp may access (= warp % 4)
         const int hsel = ew >> 2;                // which column chunks of the tile this warp owns
@@ -368,6 +407,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 __global__ void splitk_reduce_kernel(const float* __restrict__ partials, long long split_stride, int splits, void* out,
                                      long long ldo, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
                                      long long ldr, int act, int out_fp32, int rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(rows) * cols) return;
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
@@ -433,6 +474,42 @@ int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, 
     return TEO_OK;
 }
 
+// Weights in the blocked layout [N/128][K/64][128][64] (bf16): 4-D map, box = `nblocks` consecutive 128-row tiles
+// of one k block, i.e. nblocks × 16 KiB contiguous in HBM, written to shared memory as (nblocks·128) rows × 128 B
+// under the same 128-byte swizzle as the 2-D path.
+int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, uint32_t nblocks, const CUtensorMap** out) {
+    TmapKey key{ptr, N, K, 0xB10CB10CULL, nblocks};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+        *out = &it->second;
+        return TEO_OK;
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return TEO_ERR_CUDA;
+    }
+    TEO_CHECK_ARG(N % 128 == 0 && K % 64 == 0, "blocked weight layout needs N %% 128 == 0 and K %% 64 == 0 (N=%llu K=%llu)",
+                  (unsigned long long)N, (unsigned long long)K);
+    TEO_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 127) == 0, "blocked weights must be 128-byte aligned");
+    CUtensorMap m;
+    cuuint64_t dims[4] = {64, 128, K / 64, N / 128};
+    cuuint64_t strides[3] = {128, 16384, 16384ULL * (K / 64)};
+    cuuint32_t box[4] = {64, 128, 1, nblocks};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (blocked weights) failed with CUresult %d (N %llu K %llu)", (int)r, (unsigned long long)N,
+                  (unsigned long long)K);
+        return TEO_ERR_CUDA;
+    }
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    auto ins = h->tmaps.emplace(key, m);
+    *out = &ins.first->second;
+    return TEO_OK;
+}
+
 struct GemmPlan {
     bool swap;
     int bn;
@@ -481,7 +558,7 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
         attr_set = true;
     }
     const int grid = std::min(units, h->num_sms);
-    gemm_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(*ta, *tb, *tc, *tr, g);
+    TEO_CUDA(launch_kc(PDL_GEMM, gemm_tn_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *ta, *tb, *tc, *tr, g));
     TEO_LAUNCH_CHECK("gemm_tn_kernel");
     h->launches++;
     return TEO_OK;
@@ -490,7 +567,7 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
 // Small-M GEMM that stops at the fp32 split-K partials: P[s][M][N] in `workspace`, s < *splits_out.
 // The caller's next kernel reduces them (fused with its own work) in the fixed order s = 0,1,...
 int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                              size_t workspace_bytes, int* splits_out, cudaStream_t stream) {
+                              size_t workspace_bytes, int* splits_out, cudaStream_t stream, int w_blocked) {
     TEO_CHECK_ARG(h != nullptr && splits_out != nullptr, "gemm_partials: null handle");
     TEO_CHECK_ARG(M > 0 && M <= 128 && N >= 256 && K > 0 && K % 8 == 0, "gemm_partials: needs 0 < M <= 128, N >= 256, K %% 8 == 0");
     const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
@@ -507,11 +584,14 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     g.splits = p.splits;
     g.kb_per_split = p.kb_per_split;
     g.force_partial = 1;
+    g.w_is_a = 1;
     g.C = workspace;
     g.ldc = N;
     g.split_stride = static_cast<long long>(M) * N;
     const CUtensorMap *ta, *tb;
-    TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
+    g.w_blocked = w_blocked ? 1 : 0;
+    if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
+    else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
     TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
     const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
     int rc;
@@ -526,11 +606,12 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
 }
 
 int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N,
-                     int K, const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     int K, const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream, int w_blocked) {
     TEO_CHECK_ARG(h != nullptr, "null handle");
     TEO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive size M=%d N=%d K=%d", M, N, K);
     TEO_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
-    TEO_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "gemm: leading dimension too small");
+    TEO_CHECK_ARG(lda >= K && (w_blocked || ldw >= K) && ldc >= N, "gemm: leading dimension too small");
+    TEO_CHECK_ARG(!w_blocked || (N % 128 == 0 && K % 64 == 0), "gemm: blocked weights need N %% 128 == 0 and K %% 64 == 0");
     TEO_CHECK_ARG(ldc % (ep.out_fp32 ? 4 : 8) == 0, "gemm: ldc (%d) breaks 16-byte row alignment", ldc);
     TEO_CHECK_ARG(ep.residual == nullptr || ep.ldr % 8 == 0, "gemm: ldr (%d) must be a multiple of 8", ep.ldr);
     TEO_CHECK_ARG((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: C not 16-byte aligned");
@@ -552,9 +633,12 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr;
     if (p.swap) {
         g.M = N;   // weight rows on the UMMA M dimension
+        g.w_is_a = 1;
         g.N = M;
         g.transposed = 1;
-        TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
+        g.w_blocked = w_blocked ? 1 : 0;
+        if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
+        else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
         if (p.splits > 1) {
             const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
@@ -571,7 +655,10 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         g.N = N;
         g.transposed = 0;
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, BM, &ta));
-        TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
+        g.w_blocked = (w_blocked && p.bn >= 128) ? 1 : 0;
+        TEO_CHECK_ARG(!w_blocked || p.bn >= 128, "gemm: blocked weights need N >= 128");
+        if (g.w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, p.bn / 128, &tb));
+        else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
         if (!ep.out_fp32) {           // staged TMA-store epilogue: 32-row × 64-column boxes of C (and of the residual)
             g.tma_epi = 1;
             TEO_TRY(get_tmap_bf16(h, C, M, N, ldc, 32, &tc));
@@ -593,8 +680,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         const long long total = static_cast<long long>(M) * N;
         const int threads = 256;
         const int blocks = static_cast<int>((total + threads - 1) / threads);
-        splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(workspace), total, p.splits, C,
-                                                             ldc, ep.bias, ep.residual, ep.ldr, ep.act, ep.out_fp32, M, N);
+        TEO_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, reinterpret_cast<const float*>(workspace), total,
+                          p.splits, C, static_cast<long long>(ldc), ep.bias, ep.residual, static_cast<long long>(ep.ldr), ep.act, ep.out_fp32, M, N));
         TEO_LAUNCH_CHECK("splitk_reduce_kernel");
         h->launches++;
     }
@@ -613,5 +700,42 @@ extern "C" int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* 
     ep.act = act;
     ep.out_fp32 = out_fp32;
     return launch_gemm(h, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, C, ldc, M, N, K, ep,
-                       workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                       workspace, workspace_bytes, static_cast<cudaStream_t>(stream), 0);
+}
+
+extern "C" int teo_gemm_bf16_wblocked(teo_handle* h, const void* A, int lda, const void* W_blocked, void* C, int ldc, int M, int N, int K,
+                                      const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    TEO_CHECK_ARG(A && W_blocked && C, "gemm: null operand");
+    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_GELU, "gemm: unknown activation %d", act);
+    GemmEpilogue ep;
+    ep.bias = static_cast<const bf16*>(bias);
+    ep.residual = static_cast<const bf16*>(residual);
+    ep.ldr = ldr;
+    ep.act = act;
+    ep.out_fp32 = out_fp32;
+    return launch_gemm(h, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W_blocked), K, C, ldc, M, N, K, ep, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream), 1);
+}
+
+// row-major [N,K] → blocked [N/128][K/64][128][64]
+__global__ void block_weight_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int K) {
+    const long long total = static_cast<long long>(N) * K / 8;
+    const int k8 = K / 8;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n = i / k8;
+        const int c8 = static_cast<int>(i % k8);               // 16-byte chunk along K
+        const long long nb = n / 128, r = n % 128;
+        const int kb = c8 / 8, cc = c8 % 8;
+        dst[((nb * (K / 64) + kb) * 128 + r) * 8 + cc] = src[i];
+    }
+}
+extern "C" int teo_weight_to_blocked(const void* w_rowmajor, void* w_blocked, int N, int K, void* stream) {
+    TEO_CHECK_ARG(w_rowmajor && w_blocked && w_rowmajor != w_blocked, "weight_to_blocked: bad pointers (out of place only)");
+    TEO_CHECK_ARG(N > 0 && K > 0 && N % 128 == 0 && K % 64 == 0, "weight_to_blocked: N %% 128 and K %% 64 must be 0 (N=%d K=%d)", N, K);
+    block_weight_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(w_rowmajor),
+                                                                               static_cast<uint4*>(w_blocked), N, K);
+    TEO_LAUNCH_CHECK("block_weight_kernel");
+    return TEO_OK;
 }

@@ -113,6 +113,8 @@ __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict_
                             bf16* __restrict__ out, int rows, int d, float eps, const bf16* __restrict__ cls,
                             const bf16* __restrict__ pos, int n_patches) {
     __shared__ float red[32];
+    pdl_trigger();
+    pdl_wait();
     constexpr int RPB = 128 / TPR;   // rows per 128-thread block
     const int row = blockIdx.x * RPB + threadIdx.x / TPR;
     const int t = threadIdx.x % TPR;
@@ -194,9 +196,9 @@ static int launch_norm(const bf16* in, const bf16* w, const bf16* b, bf16* out, 
     TEO_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0, "norm: rows=%d d=%d (d must be a positive multiple of 8)", rows, d);
     TEO_CHECK_ARG(d <= 128 * 8 * NORM_MAXV, "norm: d=%d exceeds %d", d, 128 * 8 * NORM_MAXV);
     if (d <= 32 * 8 * 4) {
-        norm_kernel<32, MODE><<<(rows + 3) / 4, 128, 0, stream>>>(in, w, b, out, rows, d, eps, cls, pos, n_patches);
+        TEO_CUDA(launch_k(norm_kernel<32, MODE>, dim3((rows + 3) / 4), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
     } else {
-        norm_kernel<128, MODE><<<rows, 128, 0, stream>>>(in, w, b, out, rows, d, eps, cls, pos, n_patches);
+        TEO_CUDA(launch_k(norm_kernel<128, MODE>, dim3(rows), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
     }
     TEO_LAUNCH_CHECK("norm_kernel");
     return TEO_OK;
@@ -229,6 +231,8 @@ __global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict
 
 __global__ void splice_embed_kernel(const bf16* __restrict__ embed, const bf16* __restrict__ feats, const int* __restrict__ src,
                                     bf16* __restrict__ out, int tokens, int d8) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x;
     if (row >= tokens) return;
     const int s = src[row];
@@ -335,6 +339,8 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, in
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float warp_part[RN_THREADS / 32];
     __shared__ float cta_part;
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x / RN_CLUSTER;
     const int rank = static_cast<int>(cluster.block_rank());
     const int cols = d / RN_CLUSTER;                 // columns owned by this CTA (multiple of 4)
@@ -387,6 +393,8 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, in
 // act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i])
 __global__ void reduce_swiglu_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ act, int rows,
                                      int inter) {
+    pdl_trigger();
+    pdl_wait();
     const int i4 = inter / 4;
     const long long total = static_cast<long long>(rows) * i4;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -411,6 +419,8 @@ __global__ void reduce_rope_kv_write_kernel(const float* __restrict__ P, long lo
                                             const int* __restrict__ positions, bf16* __restrict__ kv_pages,
                                             const int* __restrict__ block_table, int max_pages, int n_seqs, int n_heads, int head_dim,
                                             int page_size, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin) {
+    pdl_trigger();
+    pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= n_seqs * n_heads) return;
@@ -467,6 +477,8 @@ __global__ void argmax_step_kernel(const float* __restrict__ logits, int vocab, 
                                    int step_host, int* step_ptr, int* next_ids, int* seq_lens, int eos_id) {
     __shared__ float bv[32];
     __shared__ int bi[32];
+    pdl_trigger();
+    pdl_wait();
     const int seq = blockIdx.x;
     const float* row = logits + static_cast<size_t>(seq) * vocab;
     float best = -INFINITY;
@@ -511,6 +523,8 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
     __shared__ float redf[8];
     __shared__ uint32_t sh_prefix, sh_remaining;
     __shared__ float sh_scan[256];
+    pdl_trigger();
+    pdl_wait();
     const int seq = blockIdx.x, tid = threadIdx.x;
     const float* row = logits + static_cast<size_t>(seq) * vocab;
     // ---- k-th largest key by 4 radix passes (most significant byte first)
@@ -595,7 +609,11 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
     }
 }
 
-__global__ void bump_step_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void bump_step_kernel(int* step_ptr) {
+    pdl_trigger();
+    pdl_wait();
+    *step_ptr += 1;
+}
 
 }  // namespace teo
 
@@ -688,9 +706,8 @@ extern "C" int teo_splice_embed(const void* embed_tokens, const void* image_feat
                                 void* stream) {
     TEO_CHECK_ARG(embed_tokens && src && out, "splice_embed: null pointer");
     TEO_CHECK_ARG(tokens > 0 && d > 0 && d % 8 == 0, "splice_embed: tokens=%d d=%d", tokens, d);
-    splice_embed_kernel<<<tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(embed_tokens),
-                                                                             static_cast<const bf16*>(image_feats),
-                                                                             static_cast<const int*>(src), static_cast<bf16*>(out), tokens, d / 8);
+    TEO_CUDA(launch_k(splice_embed_kernel, dim3(tokens), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(embed_tokens),
+                      static_cast<const bf16*>(image_feats), static_cast<const int*>(src), static_cast<bf16*>(out), tokens, d / 8));
     TEO_LAUNCH_CHECK("splice_embed_kernel");
     return TEO_OK;
 }
@@ -715,7 +732,7 @@ int launch_reduce_residual_rmsnorm(const float* P, long long stride, int splits,
     TEO_CHECK_ARG(P && x && w && y && rows > 0 && splits >= 1, "reduce_residual_rmsnorm: bad arguments");
     TEO_CHECK_ARG(d > 0 && d % (RN_CLUSTER * 4) == 0 && d <= RN_CLUSTER * RN_THREADS * 4 * RN_MAXV,
                   "reduce_residual_rmsnorm: d=%d must be a multiple of %d and <= %d", d, RN_CLUSTER * 4, RN_CLUSTER * RN_THREADS * 4 * RN_MAXV);
-    reduce_residual_rmsnorm_kernel<<<rows * RN_CLUSTER, RN_THREADS, 0, stream>>>(P, stride, splits, x, w, y, d, eps);
+    TEO_CUDA(launch_k(reduce_residual_rmsnorm_kernel, dim3(rows * RN_CLUSTER), dim3(RN_THREADS), 0, stream, P, stride, splits, x, w, y, d, eps));
     TEO_LAUNCH_CHECK("reduce_residual_rmsnorm_kernel");
     return TEO_OK;
 }
@@ -723,7 +740,7 @@ int launch_reduce_swiglu(const float* P, long long stride, int splits, bf16* act
     TEO_CHECK_ARG(P && act && rows > 0 && inter > 0 && splits >= 1, "reduce_swiglu: bad arguments");
     TEO_CHECK_ARG(inter % 4 == 0, "reduce_swiglu: inter %% 4 != 0");
     const long long total = static_cast<long long>(rows) * (inter / 4);
-    reduce_swiglu_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, stream>>>(P, stride, splits, act, rows, inter);
+    TEO_CUDA(launch_k(reduce_swiglu_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, P, stride, splits, act, rows, inter));
     TEO_LAUNCH_CHECK("reduce_swiglu_kernel");
     return TEO_OK;
 }
@@ -732,9 +749,9 @@ int launch_reduce_rope_kv_write(const float* P, long long stride, int splits, vo
                                 const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
     TEO_CHECK_ARG(P && qkv && positions && kv_pages && block_table && rope_cos && rope_sin && splits >= 1, "reduce_rope_kv_write: null pointer");
     const long long warps = static_cast<long long>(n_seqs) * n_heads;
-    reduce_rope_kv_write_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
-        P, stride, splits, static_cast<bf16*>(qkv), positions, static_cast<bf16*>(kv_pages), block_table, max_pages, n_seqs, n_heads, head_dim,
-        page_size, rope_cos, rope_sin);
+    TEO_CUDA(launch_k(reduce_rope_kv_write_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, stream, P, stride, splits,
+                      static_cast<bf16*>(qkv), positions, static_cast<bf16*>(kv_pages), block_table, max_pages, n_seqs, n_heads, head_dim, page_size,
+                      rope_cos, rope_sin));
     TEO_LAUNCH_CHECK("reduce_rope_kv_write_kernel");
     return TEO_OK;
 }
@@ -743,11 +760,11 @@ int launch_sample_step(const float* logits, int vocab, float temperature, int to
     TEO_CHECK_ARG(logits && finished && tokens && next_ids, "sample_step: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0 && temperature > 0.f, "sample_step: bad sizes / temperature");
     if (top_k <= 0 || top_k > vocab) top_k = vocab;
-    sample_step_kernel<<<n_seqs, 256, 0, stream>>>(logits, vocab, 1.0f / temperature, top_k, seed, finished, tokens, max_new, step_host, step_ptr,
-                                                   next_ids, seq_lens, eos_id);
+    TEO_CUDA(launch_k(sample_step_kernel, dim3(n_seqs), dim3(256), 0, stream, logits, vocab, 1.0f / temperature, top_k, seed, finished, tokens, max_new,
+                      step_host, static_cast<const int*>(step_ptr), next_ids, seq_lens, eos_id));
     TEO_LAUNCH_CHECK("sample_step_kernel");
     if (step_ptr) {
-        bump_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+        TEO_CUDA(launch_k(bump_step_kernel, dim3(1), dim3(1), 0, stream, step_ptr));
         TEO_LAUNCH_CHECK("bump_step_kernel");
     }
     return TEO_OK;
@@ -756,10 +773,11 @@ int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* t
                        int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream) {
     TEO_CHECK_ARG(logits && finished && tokens && next_ids, "argmax_step: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0, "argmax_step: bad sizes");
-    argmax_step_kernel<<<n_seqs, 1024, 0, stream>>>(logits, vocab, finished, tokens, max_new, step_host, step_ptr, next_ids, seq_lens, eos_id);
+    TEO_CUDA(launch_k(argmax_step_kernel, dim3(n_seqs), dim3(1024), 0, stream, logits, vocab, finished, tokens, max_new, step_host, step_ptr, next_ids,
+                      seq_lens, eos_id));
     TEO_LAUNCH_CHECK("argmax_step_kernel");
     if (step_ptr) {
-        bump_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+        TEO_CUDA(launch_k(bump_step_kernel, dim3(1), dim3(1), 0, stream, step_ptr));
         TEO_LAUNCH_CHECK("bump_step_kernel");
     }
     return TEO_OK;

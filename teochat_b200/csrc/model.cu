@@ -4,6 +4,7 @@
 // decode step can be captured in a CUDA graph.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -12,6 +13,16 @@
 namespace teo {
 
 static thread_local char g_err[512] = "";
+static thread_local bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
+int pdl_mask() {
+    static int mask = [] {
+        const char* e = getenv("TEO_PDL_MASK");
+        return e ? atoi(e) : 7;
+    }();
+    return mask;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -106,6 +117,11 @@ extern "C" int teo_set_sampling(teo_handle* h, float temperature, int top_k, uin
     h->sample_seed = seed;
     return TEO_OK;
 }
+extern "C" int teo_set_pdl(teo_handle* h, int enabled) {
+    TEO_CHECK_ARG(h != nullptr, "teo_set_pdl: null handle");
+    h->pdl = enabled != 0;
+    return TEO_OK;
+}
 extern "C" unsigned long long teo_launch_count(const teo_handle* h) { return h ? h->launches : 0ULL; }
 
 // ------------------------------------------------------------------------------ ViT
@@ -153,7 +169,7 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     else TEO_TRY(teo_patchify_f32_nchw(pixel_values, patches, n_frames, m->image, m->patch, m->kpad, stream));
     GemmEpilogue none;
     TEO_TRY(launch_gemm(h, patches, m->kpad, static_cast<const bf16*>(m->patch_w), m->kpad, patch_out, d, n_frames * np, d, m->kpad,
-                        none, nullptr, 0, stream));
+                        none, nullptr, 0, stream, m->w_blocked));
     TEO_TRY(teo_vit_assemble_preln(patch_out, m->cls, m->pos, m->pre_ln_w, m->pre_ln_b, hidden, n_frames, np, d, m->eps, stream));
     fill_cu_seqlens_kernel<<<(n_frames + 256) / 256, 256, 0, stream>>>(cu, n_frames, np + 1);
     TEO_LAUNCH_CHECK("fill_cu_seqlens_kernel");
@@ -164,25 +180,25 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
         TEO_TRY(teo_layernorm(hidden, L.ln1_w, L.ln1_b, ln_out, rows, d, m->eps, stream));
         GemmEpilogue e1;
         e1.bias = static_cast<const bf16*>(L.qkv_b);
-        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, nullptr, 0, stream));
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, nullptr, 0, stream, m->w_blocked));
         TEO_TRY(launch_flash_attention(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, m->heads, hd, scale,
                                        0, stream));
         GemmEpilogue e2;
         e2.bias = static_cast<const bf16*>(L.out_b);
         e2.residual = hidden;
         e2.ldr = d;
-        TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, nullptr, 0, stream));
+        TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, nullptr, 0, stream, m->w_blocked));
         TEO_TRY(teo_layernorm(hidden, L.ln2_w, L.ln2_b, ln_out, rows, d, m->eps, stream));
         GemmEpilogue e3;
         e3.bias = static_cast<const bf16*>(L.fc1_b);
         e3.act = m->act;
-        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.fc1_w), d, mlp, m->inter, rows, m->inter, d, e3, nullptr, 0, stream));
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.fc1_w), d, mlp, m->inter, rows, m->inter, d, e3, nullptr, 0, stream, m->w_blocked));
         GemmEpilogue e4;
         e4.bias = static_cast<const bf16*>(L.fc2_b);
         e4.residual = hidden;
         e4.ldr = d;
         TEO_TRY(launch_gemm(h, mlp, m->inter, static_cast<const bf16*>(L.fc2_w), m->inter, hidden, d, rows, d, m->inter, e4, nullptr, 0,
-                            stream));
+                            stream, m->w_blocked));
         h->launches += 3;
     }
     TEO_TRY(teo_vit_drop_cls(hidden, feats, n_frames, np, d, stream));
@@ -213,11 +229,11 @@ extern "C" int teo_projector_mlp2x(teo_handle* h, const teo_projector* p, const 
     e0.bias = static_cast<const bf16*>(p->b0);
     e0.act = TEO_ACT_GELU;
     TEO_TRY(launch_gemm(h, static_cast<const bf16*>(feats), p->in_dim, static_cast<const bf16*>(p->w0), p->in_dim, mid, p->hidden, rows,
-                        p->hidden, p->in_dim, e0, gw, gws, stream));
+                        p->hidden, p->in_dim, e0, gw, gws, stream, p->w_blocked));
     GemmEpilogue e1;
     e1.bias = static_cast<const bf16*>(p->b2);
     TEO_TRY(launch_gemm(h, mid, p->hidden, static_cast<const bf16*>(p->w2), p->hidden, out, p->hidden, rows, p->hidden, p->hidden, e1, gw,
-                        gws, stream));
+                        gws, stream, p->w_blocked));
     return TEO_OK;
 }
 
@@ -258,12 +274,12 @@ static int llama_layer_mlp(teo_handle* h, const teo_llama_model* m, const teo_ll
     TEO_TRY(teo_rmsnorm(x, L.post_norm, norm_out, rows, hd, m->eps, stream));
     GemmEpilogue none;
     TEO_TRY(launch_gemm(h, norm_out, hd, static_cast<const bf16*>(L.gate_up_w), hd, gate_up, 2 * I, rows, 2 * I, hd, none, gws, gws_bytes,
-                        stream));
+                        stream, m->w_blocked));
     TEO_TRY(teo_swiglu(gate_up, act, rows, I, stream));
     GemmEpilogue res;
     res.residual = x;
     res.ldr = hd;
-    TEO_TRY(launch_gemm(h, act, I, static_cast<const bf16*>(L.down_w), I, x, hd, rows, hd, I, res, gws, gws_bytes, stream));
+    TEO_TRY(launch_gemm(h, act, I, static_cast<const bf16*>(L.down_w), I, x, hd, rows, hd, I, res, gws, gws_bytes, stream, m->w_blocked));
     h->launches += 2;
     return TEO_OK;
 }
@@ -291,7 +307,7 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
         TEO_TRY(teo_rmsnorm(x, L.in_norm, w.norm_out, tokens, hdim, m->eps, stream));
         GemmEpilogue none;
         TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, tokens, 3 * hdim, hdim, none,
-                            w.gemm_ws, w.gemm_ws_bytes, stream));
+                            w.gemm_ws, w.gemm_ws_bytes, stream, m->w_blocked));
         TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(positions), static_cast<const int*>(seq_ids), L.kv_pages,
                                      static_cast<const int*>(block_table), max_pages, tokens, m->heads, hd, m->page_size,
                                      static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin), stream));
@@ -301,7 +317,7 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
         res.residual = x;
         res.ldr = hdim;
         TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, x, hdim, tokens, hdim, hdim, res, w.gemm_ws,
-                            w.gemm_ws_bytes, stream));
+                            w.gemm_ws_bytes, stream, m->w_blocked));
         h->launches += 3;
         TEO_TRY(llama_layer_mlp(h, m, L, x, tokens, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
     }
@@ -312,7 +328,7 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
     GemmEpilogue lg;
     lg.out_fp32 = 1;
     TEO_TRY(launch_gemm(h, w.last_norm, hdim, static_cast<const bf16*>(m->lm_head), hdim, logits, m->vocab, n_seqs, m->vocab, hdim, lg,
-                        w.gemm_ws, w.gemm_ws_bytes, stream));
+                        w.gemm_ws, w.gemm_ws_bytes, stream, m->w_blocked));
     h->launches += 2;
     return TEO_OK;
 }
@@ -366,6 +382,10 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     }
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     const int I = m->inter;
+    struct PdlScope {           // programmatic dependent launch for every kernel of the step (see common.h)
+        explicit PdlScope(bool on) { set_pdl(on); }
+        ~PdlScope() { set_pdl(false); }
+    } pdl_scope(h->pdl);
     const bool fused = n_seqs <= 128 && hdim >= 256 && hdim % 32 == 0 && hdim <= 8192 && I % 4 == 0;   // swap-AB split-K regime of the GEMM
     TEO_TRY(teo_splice_embed(m->embed, nullptr, next_ids, w.x, n_seqs, hdim, stream));
     TEO_TRY(teo_rmsnorm(w.x, m->layer[0].in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
@@ -378,7 +398,7 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
             int sp = 1;
             // qkv: GEMM partials → reduce + RoPE + KV-page write (position of the new token = tokens cached so far)
             TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, n_seqs, 3 * hdim, hdim, w.gemm_ws,
-                                         w.gemm_ws_bytes, &sp, stream));
+                                         w.gemm_ws_bytes, &sp, stream, m->w_blocked));
             TEO_TRY(launch_reduce_rope_kv_write(P, static_cast<long long>(n_seqs) * 3 * hdim, sp, w.qkv, static_cast<const int*>(seq_lens),
                                                 L.kv_pages, static_cast<const int*>(block_table), max_pages, n_seqs, m->heads, hd,
                                                 m->page_size, static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin),
@@ -388,23 +408,23 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
                                             max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
             // o_proj partials → reduce + residual + post-attention RMSNorm
             TEO_TRY(launch_gemm_partials(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, n_seqs, hdim, hdim, w.gemm_ws, w.gemm_ws_bytes,
-                                         &sp, stream));
+                                         &sp, stream, m->w_blocked));
             TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(L.post_norm),
                                                    w.norm_out, n_seqs, hdim, m->eps, stream));
             // gate/up partials → reduce + SwiGLU
             TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
-                                         w.gemm_ws_bytes, &sp, stream));
+                                         w.gemm_ws_bytes, &sp, stream, m->w_blocked));
             TEO_TRY(launch_reduce_swiglu(P, static_cast<long long>(n_seqs) * 2 * I, sp, w.act, n_seqs, I, stream));
             // down_proj partials → reduce + residual + the NEXT layer's input RMSNorm (or the final norm)
             TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &sp,
-                                         stream));
+                                         stream, m->w_blocked));
             TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(next_norm),
                                                    w.norm_out, n_seqs, hdim, m->eps, stream));
             h->launches += 4;
         } else {
             GemmEpilogue none;
             TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, w.qkv, 3 * hdim, n_seqs, 3 * hdim, hdim, none,
-                                w.gemm_ws, w.gemm_ws_bytes, stream));
+                                w.gemm_ws, w.gemm_ws_bytes, stream, m->w_blocked));
             TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(seq_lens), nullptr, L.kv_pages, static_cast<const int*>(block_table),
                                          max_pages, n_seqs, m->heads, hd, m->page_size, static_cast<const float*>(m->rope_cos),
                                          static_cast<const float*>(m->rope_sin), stream));
@@ -415,7 +435,7 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
             res.residual = w.x;
             res.ldr = hdim;
             TEO_TRY(launch_gemm(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, w.x, hdim, n_seqs, hdim, hdim, res, w.gemm_ws,
-                                w.gemm_ws_bytes, stream));
+                                w.gemm_ws_bytes, stream, m->w_blocked));
             h->launches += 1;
             TEO_TRY(llama_layer_mlp(h, m, L, w.x, n_seqs, w.norm_out, w.gate_up, w.act, w.gemm_ws, w.gemm_ws_bytes, stream));
             TEO_TRY(teo_rmsnorm(w.x, next_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
@@ -425,7 +445,7 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     GemmEpilogue lg;
     lg.out_fp32 = 1;
     TEO_TRY(launch_gemm(h, w.norm_out, hdim, static_cast<const bf16*>(m->lm_head), hdim, logits, m->vocab, n_seqs, m->vocab, hdim, lg,
-                        w.gemm_ws, w.gemm_ws_bytes, stream));
+                        w.gemm_ws, w.gemm_ws_bytes, stream, m->w_blocked));
     if (h->temperature > 0.f)
         TEO_TRY(launch_sample_step(static_cast<const float*>(logits), m->vocab, h->temperature, h->top_k, h->sample_seed,
                                    static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new, 0, static_cast<int*>(step_ptr),

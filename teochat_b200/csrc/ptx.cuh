@@ -25,6 +25,11 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Both are no-ops when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -74,6 +79,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 4-D tiled load (blocked weight layout [n_blk][k_blk][128][64]: one box = one or two contiguous 16 KiB tiles).
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 // 2-D tiled store shared→global (bulk async group; out-of-bounds part of the box is clipped).

@@ -53,8 +53,10 @@ class TeoModel:
         self._h = h
         self._ws_cache: Dict[str, torch.Tensor] = {}
         self._kv_pool: Optional[torch.Tensor] = None
+        self._decode_states: Dict[tuple, SimpleNamespace] = {}
         self._build_structs()
         self.use_graph = os.environ.get("TEO_NO_GRAPH", "0") != "1"
+        self.set_pdl(os.environ.get("TEO_NO_PDL", "0") != "1")
         self.last_timings: Dict[str, float] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -65,6 +67,11 @@ class TeoModel:
                 self._h = None
         except Exception:
             pass
+
+    def set_pdl(self, enabled: bool):
+        """Programmatic dependent launch inside the decode step (default on; results are identical)."""
+        self.use_pdl = bool(enabled)
+        L.check(self.lib.teo_set_pdl(self._h, 1 if enabled else 0), "teo_set_pdl")
 
     def get_image_tower(self):
         return self
@@ -97,11 +104,13 @@ class TeoModel:
         self._vit = L.VitModel(hidden=v.hidden_size, inter=v.intermediate_size, heads=v.num_attention_heads,
                                image=v.image_size, patch=v.patch_size, kpad=self.w.kpad,
                                act=L.ACT_BY_NAME[v.hidden_act], layers_run=n_run, eps=v.layer_norm_eps,
+                               w_blocked=int(bool(self.w.blocked.get("vit"))),
                                patch_w=p("vit.patch_w"), cls=p("vit.cls"), pos=p("vit.pos"),
                                pre_ln_w=p("vit.pre_ln_w"), pre_ln_b=p("vit.pre_ln_b"), layers=self._vit_layers)
         if cfg.mm_projector_type != "mlp2x_gelu":
             raise ValueError(f"Unknown projector type: {cfg.mm_projector_type}")   # projector/builder.py:51
-        self._proj = L.Projector(in_dim=v.hidden_size, hidden=l.hidden_size, w0=p("proj.w0"), b0=p("proj.b0"),
+        self._proj = L.Projector(in_dim=v.hidden_size, hidden=l.hidden_size, w_blocked=int(bool(self.w.blocked.get("proj"))),
+                                 w0=p("proj.w0"), b0=p("proj.b0"),
                                  w2=p("proj.w2"), b2=p("proj.b2"))
         # RoPE tables exactly as HF builds cos_cached/sin_cached (fp32, on the host)
         hd = l.head_dim
@@ -117,6 +126,7 @@ class TeoModel:
         self._llama = L.LlamaModel(hidden=l.hidden_size, inter=l.intermediate_size, heads=l.num_attention_heads,
                                    layers=l.num_hidden_layers, vocab=l.vocab_size, page_size=cfg.kv_page_size,
                                    rope_max_pos=self.rope_max_pos, eps=l.rms_norm_eps,
+                                   w_blocked=int(bool(self.w.blocked.get("llama"))),
                                    rope_cos=self._rope_cos.data_ptr(), rope_sin=self._rope_sin.data_ptr(),
                                    embed=p("llama.embed"), final_norm=p("llama.final_norm"),
                                    lm_head=p("llama.lm_head"), layer=self._llama_layers)
@@ -277,22 +287,40 @@ class TeoModel:
         o = 3 * T
         d_cu = meta_d[o:o + B + 1]; o += B + 1
         d_last = meta_d[o:o + B]; o += B
-        d_len = meta_d[o:o + B].clone(); o += B           # becomes the live seq_lens
-        d_bt = meta_d[o:o + B * max_pages]
+        d_len0 = meta_d[o:o + B]; o += B
+        d_bt0 = meta_d[o:o + B * max_pages]
         h = l.hidden_size
+        # ---- per-shape decode state with stable addresses, so the captured decode graph is reused across calls
+        dwb = self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len)
+        dws = self._ws("decode", dwb)
+        key = (B, max_new_tokens, max_pages, total_len, eos, sampling, float(temperature or 0.0), int(top_k), int(seed), self.use_pdl)
+        st = self._decode_states.get(key)
+        if st is None or st.pool_ptr != self._kv_pool.data_ptr() or st.dws_ptr != dws.data_ptr():
+            with torch.inference_mode(False):     # cached across calls: must stay ordinary tensors (callers may use inference_mode)
+                st = SimpleNamespace(
+                    d_len=torch.empty(B, dtype=torch.int32, device=dev), d_bt=torch.empty(B * max_pages, dtype=torch.int32, device=dev),
+                    logits=torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev),
+                    finished=torch.empty(B, dtype=torch.uint8, device=dev), tokens=torch.empty(B, max_new_tokens, dtype=torch.int32, device=dev),
+                    next_ids=torch.empty(B, dtype=torch.int32, device=dev), step_ptr=torch.empty(1, dtype=torch.int32, device=dev),
+                    graph=None, pool_ptr=self._kv_pool.data_ptr(), dws_ptr=dws.data_ptr())
+            if len(self._decode_states) >= 4:
+                self._decode_states.pop(next(iter(self._decode_states)))
+            self._decode_states[key] = st
+        d_len, d_bt, logits = st.d_len, st.d_bt, st.logits
+        finished, tokens, next_ids, step_ptr = st.finished, st.tokens, st.next_ids, st.step_ptr
+        d_len.copy_(d_len0)
+        d_bt.copy_(d_bt0)
+        finished.zero_()
+        tokens.fill_(-1)
+        step_ptr.fill_(1)
         x = self._ws("x", T * h * 2)
         L.check(self.lib.teo_splice_embed(self.w.t["llama.embed"].data_ptr(), proj.data_ptr(), d_src.data_ptr(), x.data_ptr(), T, h,
                                           stream), "teo_splice_embed")
-        logits = torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev)
         pwb = self.lib.teo_llama_prefill_workspace_bytes(C.byref(self._llama), T, B)
         pws = self._ws("prefill", pwb)
         L.check(self.lib.teo_llama_prefill(self._h, C.byref(self._llama), x.data_ptr(), T, d_cu.data_ptr(), d_pos.data_ptr(),
                                            d_sid.data_ptr(), d_last.data_ptr(), B, max_len, d_bt.data_ptr(), max_pages,
                                            logits.data_ptr(), pws.data_ptr(), pws.numel(), stream), "teo_llama_prefill")
-        finished = torch.zeros(B, dtype=torch.uint8, device=dev)
-        tokens = torch.full((B, max_new_tokens), -1, dtype=torch.int32, device=dev)
-        next_ids = torch.empty(B, dtype=torch.int32, device=dev)
-        step_ptr = torch.ones(1, dtype=torch.int32, device=dev)
         if sampling:
             L.check(self.lib.teo_sample_step(logits.data_ptr(), l.vocab_size, float(temperature), int(top_k), C.c_uint64(seed & (2 ** 64 - 1)),
                                              finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0, next_ids.data_ptr(), B, eos, stream),
@@ -303,10 +331,8 @@ class TeoModel:
         step_logits = [logits.clone()] if return_logits else None
         if ev:
             ev[2].record()
-        # ---- decode: one captured step, replayed
-        dwb = self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len)
-        dws = self._ws("decode", dwb)
 
+        # ---- decode: one captured step, replayed (the graph is cached with the state above)
         def step():
             L.check(self.lib.teo_llama_decode_step(self._h, C.byref(self._llama), next_ids.data_ptr(), d_len.data_ptr(),
                                                    finished.data_ptr(), tokens.data_ptr(), max_new_tokens, step_ptr.data_ptr(), B,
@@ -314,20 +340,19 @@ class TeoModel:
                                                    dws.numel(), self._stream()), "teo_llama_decode_step")
 
         n_steps = max_new_tokens - 1
-        graph = None
         done = 0
-        if n_steps > 0:
-            step()                      # first step eagerly (also warms function attributes / tensor maps)
+        use_graph = self.use_graph and not return_logits
+        if use_graph and st.graph is None and n_steps >= 5:
+            step()                      # first step eagerly (warms function attributes / tensor maps), then capture once
             done = 1
-            if return_logits:
-                step_logits.append(logits.clone())
-        if self.use_graph and not return_logits and n_steps - done >= 4:
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             cap_stream = torch.cuda.Stream(device=dev)
             cap_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.graph(graph, stream=cap_stream):
                 step()
+            st.graph = graph
+        graph = st.graph if use_graph else None
         while done < n_steps:
             if graph is not None:
                 graph.replay()

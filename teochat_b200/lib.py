@@ -30,12 +30,12 @@ class VitLayer(C.Structure):
 class VitModel(C.Structure):
     _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("image", C.c_int),
                 ("patch", C.c_int), ("kpad", C.c_int), ("act", C.c_int), ("layers_run", C.c_int),
-                ("eps", C.c_float), ("patch_w", vp), ("cls", vp), ("pos", vp), ("pre_ln_w", vp),
+                ("eps", C.c_float), ("w_blocked", C.c_int), ("patch_w", vp), ("cls", vp), ("pos", vp), ("pre_ln_w", vp),
                 ("pre_ln_b", vp), ("layers", C.POINTER(VitLayer))]
 
 
 class Projector(C.Structure):
-    _fields_ = [("in_dim", C.c_int), ("hidden", C.c_int), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
+    _fields_ = [("in_dim", C.c_int), ("hidden", C.c_int), ("w_blocked", C.c_int), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
 
 
 class LlamaLayer(C.Structure):
@@ -45,7 +45,7 @@ class LlamaLayer(C.Structure):
 class LlamaModel(C.Structure):
     _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
                 ("vocab", C.c_int), ("page_size", C.c_int), ("rope_max_pos", C.c_int), ("eps", C.c_float),
-                ("rope_cos", vp), ("rope_sin", vp), ("embed", vp), ("final_norm", vp), ("lm_head", vp),
+                ("w_blocked", C.c_int), ("rope_cos", vp), ("rope_sin", vp), ("embed", vp), ("final_norm", vp), ("lm_head", vp),
                 ("layer", C.POINTER(LlamaLayer))]
 
 
@@ -62,6 +62,8 @@ _SIGS = {
     "teo_init_u8_hash": (i, [vp, sz, u64, vp]),
     "teo_gemm_workspace_bytes": (sz, [i, i, i]),
     "teo_gemm_bf16": (i, [vp, vp, i, vp, i, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]),
+    "teo_gemm_bf16_wblocked": (i, [vp, vp, i, vp, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]),
+    "teo_weight_to_blocked": (i, [vp, vp, i, i, vp]),
     "teo_patchify_u8_nhwc": (i, [vp, vp, i, i, i, i, vp]),
     "teo_patchify_f32_nchw": (i, [vp, vp, i, i, i, i, vp]),
     "teo_vit_assemble_preln": (i, [vp, vp, vp, vp, vp, vp, i, i, i, f, vp]),
@@ -77,6 +79,7 @@ _SIGS = {
     "teo_argmax_step": (i, [vp, i, vp, vp, i, i, vp, i, i, vp]),
     "teo_sample_step": (i, [vp, i, f, i, u64, vp, vp, i, i, vp, i, i, vp]),
     "teo_set_sampling": (i, [vp, f, i, u64]),
+    "teo_set_pdl": (i, [vp, i]),
     "teo_vit_workspace_bytes": (sz, [C.POINTER(VitModel), i]),
     "teo_vit_encode": (i, [vp, C.POINTER(VitModel), vp, vp, i, vp, vp, sz, vp]),
     "teo_projector_workspace_bytes": (sz, [C.POINTER(Projector), i]),

@@ -132,6 +132,7 @@ class TeoWeights:
         t["llama.final_norm"] = torch.empty(h, **bf)
         t["llama.lm_head"] = torch.empty(l.vocab_size, h, **bf)
         self.t = t
+        self.blocked: Dict[str, bool] = {}
 
     # HF name → destination view (contiguous row slice of a fused buffer), or None for patch_w
     def _dest(self, name: str) -> Optional[torch.Tensor]:
@@ -197,7 +198,7 @@ class TeoWeights:
                                                   hash_scale(std), float(mean), stream), f"init {name}")
             if tmp is not None:
                 self.t["vit.patch_w"][:, :pdim] = tmp
-        return self
+        return self.to_blocked()
 
     @classmethod
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], cfg: TeoConfig, device) -> "TeoWeights":
@@ -216,6 +217,29 @@ class TeoWeights:
                 self.t["vit.patch_w"][:, :pdim] = src.reshape(shape[0], pdim)
             else:
                 dst.copy_(src.reshape(dst.shape))
+        return self.to_blocked()
+
+    # ---- blocked GEMM-weight layout (include/teochat_b200.h: teo_weight_to_blocked) -----------------------
+    def _gemm_weight_groups(self):
+        v, l = self.cfg.vision, self.cfg.llama
+        vit = ["vit.patch_w"] + [f"vit.{i}.{n}" for i in range(v.num_hidden_layers) for n in ("qkv_w", "out_w", "fc1_w", "fc2_w")]
+        proj = ["proj.w0", "proj.w2"]
+        llama = [f"llama.{i}.{n}" for i in range(l.num_hidden_layers) for n in ("qkv_w", "o_w", "gate_up_w", "down_w")] + ["llama.lm_head"]
+        return {"vit": vit, "proj": proj, "llama": llama}
+
+    def to_blocked(self) -> "TeoWeights":
+        """Re-lay every GEMM weight [N,K] as [N/128][K/64][128][64] (16 KiB contiguous operand tiles) when all
+        matrices of a model part allow it; sets ``self.blocked[part]``.  Idempotent."""
+        for part, keys in self._gemm_weight_groups().items():
+            if self.blocked.get(part):
+                continue
+            ok = all(self.t[k].shape[0] % 128 == 0 and self.t[k].shape[1] % 64 == 0 for k in keys)
+            if ok:
+                for k in keys:
+                    w = self.t[k]
+                    n, kk = w.shape
+                    self.t[k] = w.view(n // 128, 128, kk // 64, 64).permute(0, 2, 1, 3).contiguous().view(n, kk)
+            self.blocked[part] = ok
         return self
 
     def nbytes(self) -> int:

@@ -187,6 +187,13 @@ def test_graph_replay_equals_eager(tiny):
     b = model.generate_batch(ids, frames_u8=frames, max_new_tokens=20)
     model.use_graph = True
     assert a == b                  # same kernels, same order: bit-identical
+    model.set_pdl(False)           # programmatic dependent launch only changes when kernels start, not what they compute
+    c = model.generate_batch(ids, frames_u8=frames, max_new_tokens=20)
+    model.use_graph = False
+    d = model.generate_batch(ids, frames_u8=frames, max_new_tokens=20)
+    model.use_graph = True
+    model.set_pdl(True)
+    assert a == c == d
 
 
 def test_truncation_and_errors(tiny):

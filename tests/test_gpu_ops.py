@@ -331,3 +331,24 @@ def test_sample_step_distribution(teo):
         L.check(lib.teo_sample_step(tie.data_ptr(), 64, 1.0, 2, C.c_uint64(sd), fin4.data_ptr(), t4.data_ptr(), 2, 0, n4.data_ptr(), 4, 2, stream()))
         seen |= set(t4[:, 0].tolist())
     assert seen == {10, 20, 30}
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (257 * 3, 3072, 640), (32, 4096, 4096), (5, 512, 256), (1000, 128, 192), (64, 22016, 4096)])
+def test_gemm_blocked_weights(teo, M, N, K):
+    """Blocked weight layout [N/128][K/64][128][64]: relayout is a pure permutation, and the GEMM gives the same
+    result as with the row-major weights (normal tiles, swap-AB and split-K schedules)."""
+    lib, h = teo
+    A, W = bf(rnd(M, K, seed=1)), bf(rnd(N, K, scale=K ** -0.5, seed=2))
+    bias, res = bf(rnd(N, seed=5)), bf(rnd(M, N, seed=6))
+    Wb = torch.empty_like(W)
+    L.check(lib.teo_weight_to_blocked(W.data_ptr(), Wb.data_ptr(), N, K, stream()))
+    assert torch.equal(Wb.view(N // 128, K // 64, 128, 64), W.view(N // 128, 128, K // 64, 64).permute(0, 2, 1, 3))
+    ref = gemm(teo, A, W, bias=bias, residual=res, act=1)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    wsb = lib.teo_gemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
+    L.check(lib.teo_gemm_bf16_wblocked(h, A.data_ptr(), K, Wb.data_ptr(), out.data_ptr(), N, M, N, K, bias.data_ptr(), res.data_ptr(), N, 1, 0,
+                                       ws.data_ptr(), ws.numel(), stream()))
+    assert torch.equal(out, ref)            # same tiles, same accumulation order: bit-identical
+    rc = lib.teo_weight_to_blocked(W.data_ptr(), Wb.data_ptr(), N, K + 8, stream())
+    assert rc == -1
