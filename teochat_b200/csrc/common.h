@@ -131,8 +131,24 @@ struct GemmEpilogue {
 int launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
                 const GemmEpilogue& ep, void* workspace, size_t workspace_bytes, cudaStream_t stream, int w_blocked = 0);
 
-// Small-M (decode) GEMM that stops at fp32 split-K partials P[s][M][N]; the consumer kernel reduces them.
+// fp32 partial sums left by the small-M (stream-K) GEMM schedule: P[slot][row][col], slot < partial_count(col).
+// CTA c of that schedule owns k-blocks [c·q, (c+1)·q) of the flattened (128-column tile, k-block) space, so the
+// column tile t = col/128 was touched by CTAs (t·kb)/q … ((t+1)·kb − 1)/q, one slot each.
+struct PartialInfo {
+    const float* P;
+    long long stride;     // elements between slots (= rows · cols)
+    int kb, q, grid;
+};
+__host__ __device__ inline int partial_count(const PartialInfo& pi, int col) {
+    const int t = col >> 7;                       // tiles·kb < 2^31 for every shape here (≤ 250 tiles × 172 k-blocks)
+    const int first = (t * pi.kb) / pi.q;
+    int last = ((t + 1) * pi.kb - 1) / pi.q;
+    if (last > pi.grid - 1) last = pi.grid - 1;
+    return last - first + 1;
+}
+
+// Small-M (decode) GEMM that stops at the fp32 partials; the consumer kernel reduces them (fixed slot order).
 int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                         size_t workspace_bytes, int* splits_out, cudaStream_t stream, int w_blocked = 0);
+                         size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked = 0);
 
 }  // namespace teo

@@ -53,11 +53,11 @@ struct GemmArgs {
     int act;
     int out_fp32;
     int transposed;             // store C[n*ldc + m], bias indexed by m (swap-AB)
-    int splits;                 // split-K factor; > 1 → fp32 partials, no bias/act/residual here
-    long long split_stride;     // elements between partials
-    int kb_per_split;           // K blocks per split
+    int streamk;                // small-M schedule: every CTA takes an equal contiguous share of the flattened
+                                // (tile, k-block) space; fp32 partials per (tile, slot), no bias/act/residual here
+    int sk_q;                   // k-blocks per CTA in that schedule
+    long long split_stride;     // elements between partial slots
     int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
-    int force_partial;          // write fp32 partials even when splits == 1
     int w_is_a;                 // operand A holds the (constant) weights: may be fetched before griddepcontrol.wait
     int w_blocked;              // weights stored tile-blocked [N/128][K/64][128][64] (4-D tensor map)
 };
@@ -77,18 +77,54 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     return x;
 }
 
-__device__ __forceinline__ void unit_to_tile(int unit, const GemmArgs& g, int num_m, int num_n, int& m_blk, int& n_blk,
-                                             int& split) {
-    split = unit % g.splits;
-    const int tile = unit / g.splits;
-    const int group_sz = GROUP_M * num_n;
-    const int grp = tile / group_sz;
-    const int first_m = grp * GROUP_M;
-    const int gm = min(GROUP_M, num_m - first_m);
-    const int in_grp = tile - grp * group_sz;
-    m_blk = first_m + in_grp % gm;
-    n_blk = in_grp / gm;
-}
+// Work items of one CTA.  Normal schedule: whole tiles, strided over the persistent grid, rasterised in groups of
+// GROUP_M tiles along M.  Stream-K schedule (small M, weight streaming): CTA c owns k-blocks [c·Q, (c+1)·Q) of the
+// flattened (tile, k-block) space, so every SM streams the same number of weight bytes (no wave quantisation);
+// a tile touched by several CTAs gets one fp32 partial per CTA, slot = c − first CTA of the tile.
+struct WorkItem {
+    int m_blk, n_blk, kb0, kb1, slot;
+};
+struct Scheduler {
+    int num_m, num_n, total_kb;
+    int unit, num_units;          // normal
+    long long k, k_end;           // stream-K
+    __device__ __forceinline__ void init(const GemmArgs& g, int num_m_, int num_n_, int total_kb_) {
+        num_m = num_m_; num_n = num_n_; total_kb = total_kb_;
+        unit = blockIdx.x;
+        num_units = num_m * num_n;
+        if (g.streamk) {
+            const long long total = static_cast<long long>(num_units) * total_kb;
+            k = static_cast<long long>(blockIdx.x) * g.sk_q;
+            k_end = min(total, k + g.sk_q);
+        }
+    }
+    __device__ __forceinline__ bool next(const GemmArgs& g, WorkItem& it) {
+        if (g.streamk) {
+            if (k >= k_end) return false;
+            const int tile = static_cast<int>(k / total_kb);
+            it.kb0 = static_cast<int>(k - static_cast<long long>(tile) * total_kb);
+            it.kb1 = static_cast<int>(min(static_cast<long long>(total_kb), it.kb0 + (k_end - k)));
+            it.m_blk = tile / num_n;
+            it.n_blk = tile % num_n;
+            it.slot = static_cast<int>(blockIdx.x) - static_cast<int>((static_cast<long long>(tile) * total_kb) / g.sk_q);
+            k += it.kb1 - it.kb0;
+            return true;
+        }
+        if (unit >= num_units) return false;
+        const int group_sz = GROUP_M * num_n;
+        const int grp = unit / group_sz;
+        const int first_m = grp * GROUP_M;
+        const int gm = min(GROUP_M, num_m - first_m);
+        const int in_grp = unit - grp * group_sz;
+        it.m_blk = first_m + in_grp % gm;
+        it.n_blk = in_grp / gm;
+        it.kb0 = 0;
+        it.kb1 = total_kb;
+        it.slot = 0;
+        unit += gridDim.x;
+        return true;
+    }
+};
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -113,7 +149,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int num_m = (g.M + BM - 1) / BM;
     const int num_n = (g.N + BN - 1) / BN;
-    const int num_units = num_m * num_n * g.splits;
     const int total_kb = (g.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -161,36 +196,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             // the activation tiles of those stages (each full barrier expects both).
             int pre = 0;
             {
+                Scheduler sc;
+                sc.init(g, num_m, num_n, total_kb);
+                WorkItem it;
                 int cnt = 0;
-                for (int unit = blockIdx.x; unit < num_units && cnt < STAGES; unit += gridDim.x) {
-                    int m_blk, n_blk, split;
-                    unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
-                    const int kb0 = split * g.kb_per_split;
-                    const int kb1 = min(total_kb, kb0 + g.kb_per_split);
-                    for (int kb = kb0; kb < kb1 && cnt < STAGES; ++kb, ++cnt) {
+                while (cnt < STAGES && sc.next(g, it)) {
+                    for (int kb = it.kb0; kb < it.kb1 && cnt < STAGES; ++kb, ++cnt) {
                         mbar_arrive_expect_tx(&full_bar[cnt], Cfg::STAGE_BYTES);
-                        if (g.w_is_a) load_a(cnt, kb, m_blk);
-                        else load_b(cnt, kb, n_blk);
+                        if (g.w_is_a) load_a(cnt, kb, it.m_blk);
+                        else load_b(cnt, kb, it.n_blk);
                     }
                 }
                 pre = cnt;
             }
             pdl_wait();
             int done = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                int m_blk, n_blk, split;
-                unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
-                const int kb0 = split * g.kb_per_split;
-                const int kb1 = min(total_kb, kb0 + g.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb, ++done) {
+            Scheduler sc;
+            sc.init(g, num_m, num_n, total_kb);
+            WorkItem it;
+            while (sc.next(g, it)) {
+                for (int kb = it.kb0; kb < it.kb1; ++kb, ++done) {
                     if (done < pre) {               // weights already in flight: add the other operand
-                        if (g.w_is_a) load_b(s, kb, n_blk);
-                        else load_a(s, kb, m_blk);
+                        if (g.w_is_a) load_b(s, kb, it.n_blk);
+                        else load_a(s, kb, it.m_blk);
                     } else {
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                        load_a(s, kb, m_blk);
-                        load_b(s, kb, n_blk);
+                        load_a(s, kb, it.m_blk);
+                        load_b(s, kb, it.n_blk);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -203,15 +236,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                int m_blk, n_blk, split;
-                unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
-                const int kb0 = split * g.kb_per_split;
-                const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+            Scheduler sc;
+            sc.init(g, num_m, num_n, total_kb);
+            WorkItem it;
+            while (sc.next(g, it)) {
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = it.kb0; kb < it.kb1; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
@@ -220,13 +252,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the
                         // (address >> 4) field of the descriptor
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);          // frees the ring slot when the MMAs retire
-                    if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+                    if (kb == it.kb1 - 1) umma_commit(&tfull_bar[as]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                if (kb1 <= kb0) umma_commit(&tfull_bar[as]);   // degenerate (never scheduled)
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
@@ -242,9 +273,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint32_t rph = 0;
         int as = 0;
         uint32_t aph = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-            int m_blk, n_blk, split;
-            unit_to_tile(unit, g, num_m, num_n, m_blk, n_blk, split);
+        Scheduler sc;
+        sc.init(g, num_m, num_n, total_kb);
+        WorkItem it;
+        while (sc.next(g, it)) {
+            const int m_blk = it.m_blk, n_blk = it.n_blk, split = it.slot;
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -317,7 +350,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 // ---- direct path: fp32 / split-K partial / transposed (swap-AB) outputs
                 const int m = m_blk * BM + q * 32 + lane;
                 const bool m_ok = m < g.M;
-                const bool partial = g.splits > 1 || g.force_partial;
+                const bool partial = g.streamk != 0;
 #pragma unroll 1
                 for (int c0 = hsel * 32; c0 < BN; c0 += 64) {
                     const int n0 = n_blk * BN + c0;
@@ -403,17 +436,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-// out[i] = bf16/f32( Σ_s partial[s][i] + bias[i % n] ) ... (+act) (+residual) — fixed summation order.
-__global__ void splitk_reduce_kernel(const float* __restrict__ partials, long long split_stride, int splits, void* out,
-                                     long long ldo, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
-                                     long long ldr, int act, int out_fp32, int rows, int cols) {
+// out[r,c] = act(Σ_slots partial[slot][r,c] + bias[c]) + residual[r,c] — fixed summation order (deterministic).
+__global__ void splitk_reduce_kernel(PartialInfo pi, void* out, long long ldo, const bf16* __restrict__ bias,
+                                     const bf16* __restrict__ residual, long long ldr, int act, int out_fp32, int rows, int cols) {
     pdl_trigger();
     pdl_wait();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(rows) * cols) return;
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    const int n = partial_count(pi, c);
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partials[s * split_stride + i];
+    for (int s = 0; s < n; ++s) acc += pi.P[s * pi.stride + i];
     if (bias) acc += __bfloat162float(bias[c]);
     acc = apply_act(acc, act);
     if (residual) acc += __bfloat162float(residual[r * ldr + c]);
@@ -513,24 +546,22 @@ int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, ui
 struct GemmPlan {
     bool swap;
     int bn;
-    int splits;
-    int kb_per_split;
+    int sk_q, sk_grid, sk_smax;      // stream-K schedule (swap mode)
 };
 
 static GemmPlan plan_gemm(int M, int N, int K, int num_sms) {
-    GemmPlan p;
+    GemmPlan p{};
     const int total_kb = (K + BK - 1) / BK;
     p.swap = (M <= 128) && (N >= 256);
-    p.splits = 1;
-    p.kb_per_split = total_kb;
     if (p.swap) {
         p.bn = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
         const int tiles = (N + BM - 1) / BM;
-        int want = (2 * num_sms + tiles - 1) / tiles;           // ≥ 2 work units per SM
-        want = std::max(1, std::min(want, std::max(1, total_kb / 4)));
-        want = std::min(want, 16);
-        p.kb_per_split = (total_kb + want - 1) / want;
-        p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+        const long long total = static_cast<long long>(tiles) * total_kb;
+        long long grid = std::min<long long>(num_sms, static_cast<long long>(tiles) * 16);   // ≤ ~17 partial slots per tile
+        grid = std::max<long long>(1, std::min(grid, total));
+        p.sk_q = static_cast<int>((total + grid - 1) / grid);
+        p.sk_grid = static_cast<int>((total + p.sk_q - 1) / p.sk_q);
+        p.sk_smax = (total_kb + p.sk_q - 2) / p.sk_q + 1;
     } else {
         p.bn = N >= 256 ? 256 : (N > 64 ? 128 : 64);
     }
@@ -543,9 +574,9 @@ using namespace teo;
 
 extern "C" size_t teo_gemm_workspace_bytes(int M, int N, int K) {
     GemmPlan p = plan_gemm(M, N, K, 148);
-    // independent of the SM count actually present: plan with the max split factor
     if (!p.swap) return 0;
-    return static_cast<size_t>(16) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float);
+    // upper bound on partial slots per tile for any SM count (plan_gemm caps CTAs at 16 per tile)
+    return static_cast<size_t>(19) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float);
 }
 
 template <int BN>
@@ -567,11 +598,11 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
 // Small-M GEMM that stops at the fp32 split-K partials: P[s][M][N] in `workspace`, s < *splits_out.
 // The caller's next kernel reduces them (fused with its own work) in the fixed order s = 0,1,...
 int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                              size_t workspace_bytes, int* splits_out, cudaStream_t stream, int w_blocked) {
-    TEO_CHECK_ARG(h != nullptr && splits_out != nullptr, "gemm_partials: null handle");
+                              size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked) {
+    TEO_CHECK_ARG(h != nullptr && info != nullptr, "gemm_partials: null handle");
     TEO_CHECK_ARG(M > 0 && M <= 128 && N >= 256 && K > 0 && K % 8 == 0, "gemm_partials: needs 0 < M <= 128, N >= 256, K %% 8 == 0");
     const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
-    const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
+    const size_t need = static_cast<size_t>(p.sk_smax) * M * N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need) {
         set_error("gemm_partials: need %zu workspace bytes, got %zu", need, workspace_bytes);
         return TEO_ERR_WORKSPACE;
@@ -581,9 +612,8 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     g.N = M;
     g.K = K;
     g.transposed = 1;
-    g.splits = p.splits;
-    g.kb_per_split = p.kb_per_split;
-    g.force_partial = 1;
+    g.streamk = 1;
+    g.sk_q = p.sk_q;
     g.w_is_a = 1;
     g.C = workspace;
     g.ldc = N;
@@ -593,15 +623,18 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
     else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
     TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
-    const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
     int rc;
     switch (p.bn) {
-        case 32: rc = launch_cfg<32>(h, ta, tb, ta, ta, g, units, stream); break;
-        case 64: rc = launch_cfg<64>(h, ta, tb, ta, ta, g, units, stream); break;
-        default: rc = launch_cfg<128>(h, ta, tb, ta, ta, g, units, stream); break;
+        case 32: rc = launch_cfg<32>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
+        case 64: rc = launch_cfg<64>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
+        default: rc = launch_cfg<128>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
     }
     TEO_TRY(rc);
-    *splits_out = p.splits;
+    info->P = static_cast<const float*>(workspace);
+    info->stride = static_cast<long long>(M) * N;
+    info->kb = (K + BK - 1) / BK;
+    info->q = p.sk_q;
+    info->grid = p.sk_grid;
     return TEO_OK;
 }
 
@@ -628,8 +661,6 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     g.C = C;
     g.ldc = ldc;
     g.K = K;
-    g.splits = p.splits;
-    g.kb_per_split = p.kb_per_split;
     const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr;
     if (p.swap) {
         g.M = N;   // weight rows on the UMMA M dimension
@@ -640,14 +671,16 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
         else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
-        if (p.splits > 1) {
-            const size_t need = static_cast<size_t>(p.splits) * M * N * sizeof(float);
+        {
+            const size_t need = static_cast<size_t>(p.sk_smax) * M * N * sizeof(float);
             if (workspace == nullptr || workspace_bytes < need) {
-                set_error("gemm: split-K needs %zu workspace bytes, got %zu", need, workspace_bytes);
+                set_error("gemm: small-M schedule needs %zu workspace bytes, got %zu", need, workspace_bytes);
                 return TEO_ERR_WORKSPACE;
             }
+            g.streamk = 1;
+            g.sk_q = p.sk_q;
             g.C = workspace;
-            g.ldc = N;                       // partial layout [split][M_act][N_out]
+            g.ldc = N;                       // partial layout [slot][M_act][N_out]
             g.split_stride = static_cast<long long>(M) * N;
         }
     } else {
@@ -667,7 +700,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         }
     }
     if (!g.tma_epi) tc = tr = ta;     // unused by the direct-store epilogue
-    const int units = ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn) * g.splits;
+    const int units = p.swap ? p.sk_grid : ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn);
     int rc;
     switch (p.bn) {
         case 32: rc = launch_cfg<32>(h, ta, tb, tc, tr, g, units, stream); break;
@@ -676,12 +709,13 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         default: rc = launch_cfg<256>(h, ta, tb, tc, tr, g, units, stream); break;
     }
     TEO_TRY(rc);
-    if (p.swap && p.splits > 1) {
+    if (p.swap) {
         const long long total = static_cast<long long>(M) * N;
         const int threads = 256;
         const int blocks = static_cast<int>((total + threads - 1) / threads);
-        TEO_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, reinterpret_cast<const float*>(workspace), total,
-                          p.splits, C, static_cast<long long>(ldc), ep.bias, ep.residual, static_cast<long long>(ep.ldr), ep.act, ep.out_fp32, M, N));
+        PartialInfo pi{reinterpret_cast<const float*>(workspace), total, (K + BK - 1) / BK, p.sk_q, p.sk_grid};
+        TEO_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, pi, C, static_cast<long long>(ldc), ep.bias, ep.residual,
+                          static_cast<long long>(ep.ldr), ep.act, ep.out_fp32, M, N));
         TEO_LAUNCH_CHECK("splitk_reduce_kernel");
         h->launches++;
     }

@@ -294,7 +294,7 @@ __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restri
 // fixed order s = 0,1,… and do the next element-wise stage in the same pass (same rounding points as the
 // unfused chain: the reduced value is rounded to bf16 exactly where the GEMM epilogue would have).
 // Σ_s P[s][idx] in the fixed order s = 0,1,…; loads are issued four at a time so the L2 latencies overlap.
-__device__ __forceinline__ float sum_partials(const float* __restrict__ P, long long stride, int splits, long long idx) {
+__device__ __forceinline__ float sum_partials_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
     float acc = 0.f;
     int s = 0;
     for (; s + 4 <= splits; s += 4) {
@@ -305,7 +305,7 @@ __device__ __forceinline__ float sum_partials(const float* __restrict__ P, long 
     for (; s < splits; ++s) acc += P[s * stride + idx];
     return acc;
 }
-__device__ __forceinline__ float4 sum_partials4(const float* __restrict__ P, long long stride, int splits, long long idx) {
+__device__ __forceinline__ float4 sum_partials4_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
     for (; s + 4 <= splits; s += 4) {
@@ -325,6 +325,14 @@ __device__ __forceinline__ float4 sum_partials4(const float* __restrict__ P, lon
     return acc;
 }
 
+// idx = row·cols + col; the slot count depends on the 128-column tile of `col`
+__device__ __forceinline__ float sum_partials(const PartialInfo& pi, long long idx, int col) {
+    return sum_partials_n(pi.P, pi.stride, partial_count(pi, col), idx);
+}
+__device__ __forceinline__ float4 sum_partials4(const PartialInfo& pi, long long idx, int col) {
+    return sum_partials4_n(pi.P, pi.stride, partial_count(pi, col), idx);
+}
+
 // x[row] = bf16(Σ partials + x[row]);  y[row] = RMSNorm(x[row]) * w      (o_proj / down_proj → next norm)
 // A thread-block cluster of RN_CLUSTER CTAs shares one row (bs=32 rows alone would occupy 32 of 148 SMs): each CTA
 // reduces d/RN_CLUSTER columns with 16-byte loads, the per-CTA sums of squares are exchanged through distributed
@@ -333,8 +341,7 @@ constexpr int RN_CLUSTER = 8;
 constexpr int RN_THREADS = 128;
 constexpr int RN_MAXV = 2;               // float4 groups per thread: d ≤ RN_CLUSTER · RN_THREADS · 4 · RN_MAXV = 8192
 __global__ void __cluster_dims__(RN_CLUSTER, 1, 1) __launch_bounds__(RN_THREADS)
-reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ x,
-                               const bf16* __restrict__ w, bf16* __restrict__ y, int d, float eps) {
+reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int d, float eps) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float warp_part[RN_THREADS / 32];
@@ -352,7 +359,7 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, in
         const int c = (v * RN_THREADS + threadIdx.x) * 4;
         if (c < cols) {
             const uint2 r = *reinterpret_cast<const uint2*>(x + base + c);
-            const float4 acc = sum_partials4(P, stride, splits, base + c);
+            const float4 acc = sum_partials4(pi, base + c, rank * cols + c);
             // the residual stream is stored in bf16: round before the statistics, like the unfused chain
             vals[v][0] = __bfloat162float(__float2bfloat16_rn(acc.x + bf16_lo(r.x)));
             vals[v][1] = __bfloat162float(__float2bfloat16_rn(acc.y + bf16_hi(r.x)));
@@ -391,8 +398,7 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ P, long long stride, in
 }
 
 // act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i])
-__global__ void reduce_swiglu_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ act, int rows,
-                                     int inter) {
+__global__ void reduce_swiglu_kernel(PartialInfo pi, bf16* __restrict__ act, int rows, int inter) {
     pdl_trigger();
     pdl_wait();
     const int i4 = inter / 4;
@@ -400,8 +406,8 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ P, long long stri
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / i4, c = (i % i4) * 4;
-        const float4 g = sum_partials4(P, stride, splits, r * 2 * inter + c);
-        const float4 u = sum_partials4(P, stride, splits, r * 2 * inter + inter + c);
+        const float4 g = sum_partials4(pi, r * 2 * inter + c, static_cast<int>(c));
+        const float4 u = sum_partials4(pi, r * 2 * inter + inter + c, static_cast<int>(inter + c));
         const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
         float o[4];
 #pragma unroll
@@ -415,7 +421,7 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ P, long long stri
 
 // One warp per (sequence, head): reduce the q/k/v partials, RoPE q and k, write q into the qkv buffer and k, v
 // into the KV page of position seq_lens[seq].
-__global__ void reduce_rope_kv_write_kernel(const float* __restrict__ P, long long stride, int splits, bf16* __restrict__ qkv,
+__global__ void reduce_rope_kv_write_kernel(PartialInfo pi, bf16* __restrict__ qkv,
                                             const int* __restrict__ positions, bf16* __restrict__ kv_pages,
                                             const int* __restrict__ block_table, int max_pages, int n_seqs, int n_heads, int head_dim,
                                             int page_size, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin) {
@@ -435,8 +441,16 @@ __global__ void reduce_rope_kv_write_kernel(const float* __restrict__ P, long lo
     bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim;
     const float* cs = rope_cos + static_cast<size_t>(pos) * half;
     const float* sn = rope_sin + static_cast<size_t>(pos) * half;
-    auto r2 = [&](long long off, float& a, float& b) {          // two adjacent reduced values, rounded to bf16 like the GEMM output
+    const float* P = pi.P;
+    const long long stride = pi.stride;
+    const long long row0 = static_cast<long long>(seq) * 3 * hidden;
+    // head_dim-aligned head slices never straddle a 128-column tile when head_dim divides 128 or is a multiple of it
+    const int col_q = static_cast<int>(rowbase - row0);
+    const int cnt_q = partial_count(pi, col_q), cnt_k = partial_count(pi, col_q + hidden);
+    const bool uniform = (head_dim <= 128) && (128 % head_dim == 0);
+    auto r2 = [&](long long off, float& a, float& b, int cnt_hint) {   // two adjacent reduced values, rounded to bf16 like the GEMM output
         float x0 = 0.f, x1 = 0.f;
+        const int splits = uniform ? cnt_hint : partial_count(pi, static_cast<int>(off - row0));
         int sp = 0;
         for (; sp + 4 <= splits; sp += 4) {
             const float2 p0 = *reinterpret_cast<const float2*>(P + (sp + 0) * stride + off);
@@ -455,17 +469,17 @@ __global__ void reduce_rope_kv_write_kernel(const float* __restrict__ P, long lo
     for (int i = lane * 2; i < half; i += 64) {
         const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
         float a0, a1, b0, b1;
-        r2(rowbase + i, a0, a1);
-        r2(rowbase + i + half, b0, b1);
+        r2(rowbase + i, a0, a1, cnt_q);
+        r2(rowbase + i + half, b0, b1, cnt_q);
         *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
         *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
-        r2(rowbase + hidden + i, a0, a1);
-        r2(rowbase + hidden + i + half, b0, b1);
+        r2(rowbase + hidden + i, a0, a1, cnt_k);
+        r2(rowbase + hidden + i + half, b0, b1, cnt_k);
         *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
         *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
     }
     for (int i = lane * 4; i < head_dim; i += 128) {
-        const float4 v = sum_partials4(P, stride, splits, rowbase + 2 * hidden + i);
+        const float4 v = sum_partials4(pi, rowbase + 2 * hidden + i, static_cast<int>(rowbase - row0) + 2 * hidden + i);
         *reinterpret_cast<uint2*>(vdst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
@@ -727,29 +741,28 @@ int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, vo
     TEO_LAUNCH_CHECK("rope_kv_write_kernel");
     return TEO_OK;
 }
-int launch_reduce_residual_rmsnorm(const float* P, long long stride, int splits, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps,
-                                   cudaStream_t stream) {
-    TEO_CHECK_ARG(P && x && w && y && rows > 0 && splits >= 1, "reduce_residual_rmsnorm: bad arguments");
+int launch_reduce_residual_rmsnorm(const PartialInfo& pi, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, cudaStream_t stream) {
+    TEO_CHECK_ARG(pi.P && x && w && y && rows > 0, "reduce_residual_rmsnorm: bad arguments");
     TEO_CHECK_ARG(d > 0 && d % (RN_CLUSTER * 4) == 0 && d <= RN_CLUSTER * RN_THREADS * 4 * RN_MAXV,
                   "reduce_residual_rmsnorm: d=%d must be a multiple of %d and <= %d", d, RN_CLUSTER * 4, RN_CLUSTER * RN_THREADS * 4 * RN_MAXV);
-    TEO_CUDA(launch_k(reduce_residual_rmsnorm_kernel, dim3(rows * RN_CLUSTER), dim3(RN_THREADS), 0, stream, P, stride, splits, x, w, y, d, eps));
+    TEO_CUDA(launch_k(reduce_residual_rmsnorm_kernel, dim3(rows * RN_CLUSTER), dim3(RN_THREADS), 0, stream, pi, x, w, y, d, eps));
     TEO_LAUNCH_CHECK("reduce_residual_rmsnorm_kernel");
     return TEO_OK;
 }
-int launch_reduce_swiglu(const float* P, long long stride, int splits, bf16* act, int rows, int inter, cudaStream_t stream) {
-    TEO_CHECK_ARG(P && act && rows > 0 && inter > 0 && splits >= 1, "reduce_swiglu: bad arguments");
+int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, cudaStream_t stream) {
+    TEO_CHECK_ARG(pi.P && act && rows > 0 && inter > 0, "reduce_swiglu: bad arguments");
     TEO_CHECK_ARG(inter % 4 == 0, "reduce_swiglu: inter %% 4 != 0");
     const long long total = static_cast<long long>(rows) * (inter / 4);
-    TEO_CUDA(launch_k(reduce_swiglu_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, P, stride, splits, act, rows, inter));
+    TEO_CUDA(launch_k(reduce_swiglu_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, pi, act, rows, inter));
     TEO_LAUNCH_CHECK("reduce_swiglu_kernel");
     return TEO_OK;
 }
-int launch_reduce_rope_kv_write(const float* P, long long stride, int splits, void* qkv, const int* positions, void* kv_pages,
+int launch_reduce_rope_kv_write(const PartialInfo& pi, void* qkv, const int* positions, void* kv_pages,
                                 const int* block_table, int max_pages, int n_seqs, int n_heads, int head_dim, int page_size,
                                 const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
-    TEO_CHECK_ARG(P && qkv && positions && kv_pages && block_table && rope_cos && rope_sin && splits >= 1, "reduce_rope_kv_write: null pointer");
+    TEO_CHECK_ARG(pi.P && qkv && positions && kv_pages && block_table && rope_cos && rope_sin, "reduce_rope_kv_write: null pointer");
     const long long warps = static_cast<long long>(n_seqs) * n_heads;
-    TEO_CUDA(launch_k(reduce_rope_kv_write_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, stream, P, stride, splits,
+    TEO_CUDA(launch_k(reduce_rope_kv_write_kernel, dim3(static_cast<unsigned>((warps * 32 + 255) / 256)), dim3(256), 0, stream, pi,
                       static_cast<bf16*>(qkv), positions, static_cast<bf16*>(kv_pages), block_table, max_pages, n_seqs, n_heads, head_dim, page_size,
                       rope_cos, rope_sin));
     TEO_LAUNCH_CHECK("reduce_rope_kv_write_kernel");

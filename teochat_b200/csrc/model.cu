@@ -45,10 +45,9 @@ int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* t
 
 int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
                        int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
-int launch_reduce_residual_rmsnorm(const float* P, long long stride, int splits, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps,
-                                   cudaStream_t stream);
-int launch_reduce_swiglu(const float* P, long long stride, int splits, bf16* act, int rows, int inter, cudaStream_t stream);
-int launch_reduce_rope_kv_write(const float* P, long long stride, int splits, void* qkv, const int* positions, void* kv_pages,
+int launch_reduce_residual_rmsnorm(const PartialInfo& pi, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, cudaStream_t stream);
+int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, cudaStream_t stream);
+int launch_reduce_rope_kv_write(const PartialInfo& pi, void* qkv, const int* positions, void* kv_pages,
                                 const int* block_table, int max_pages, int n_seqs, int n_heads, int head_dim, int page_size,
                                 const float* rope_cos, const float* rope_sin, cudaStream_t stream);
 
@@ -125,8 +124,18 @@ extern "C" int teo_set_pdl(teo_handle* h, int enabled) {
 extern "C" unsigned long long teo_launch_count(const teo_handle* h) { return h ? h->launches : 0ULL; }
 
 // ------------------------------------------------------------------------------ ViT
+static size_t vit_gemm_ws_bytes(const teo_vit_model* m, int n) {
+    const int g = m->image / m->patch, np = g * g, rows = n * (np + 1), d = m->hidden;
+    size_t b = teo_gemm_workspace_bytes(n * np, d, m->kpad);
+    b = std::max(b, teo_gemm_workspace_bytes(rows, 3 * d, d));
+    b = std::max(b, teo_gemm_workspace_bytes(rows, d, d));
+    b = std::max(b, teo_gemm_workspace_bytes(rows, m->inter, d));
+    b = std::max(b, teo_gemm_workspace_bytes(rows, d, m->inter));
+    return b;
+}
+
 static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patches, bf16** patch_out, bf16** hidden, bf16** ln_out,
-                            bf16** qkv, bf16** attn, bf16** mlp, int** cu) {
+                            bf16** qkv, bf16** attn, bf16** mlp, int** cu, uint8_t** gemm_ws = nullptr) {
     const int g = m->image / m->patch, np = g * g;
     const size_t rows = static_cast<size_t>(n) * (np + 1);
     Arena local(nullptr, 0);
@@ -140,6 +149,7 @@ static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patc
     p = A.take<bf16>(rows * m->hidden); if (attn) *attn = p;
     p = A.take<bf16>(rows * m->inter); if (mlp) *mlp = p;
     int* c = A.take<int>(n + 1); if (cu) *cu = c;
+    uint8_t* gw = A.take<uint8_t>(vit_gemm_ws_bytes(m, n)); if (gemm_ws) *gemm_ws = gw;   // small batches run the small-M GEMM schedule
     return A.off;
 }
 
@@ -160,7 +170,9 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     Arena A(workspace, workspace_bytes);
     bf16 *patches, *patch_out, *hidden, *ln_out, *qkv, *attn, *mlp;
     int* cu;
-    vit_ws_layout(m, n_frames, &A, &patches, &patch_out, &hidden, &ln_out, &qkv, &attn, &mlp, &cu);
+    uint8_t* gws;
+    vit_ws_layout(m, n_frames, &A, &patches, &patch_out, &hidden, &ln_out, &qkv, &attn, &mlp, &cu, &gws);
+    const size_t gws_bytes = vit_gemm_ws_bytes(m, n_frames);
     if (!A.ok) {
         set_error("vit_encode: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
         return TEO_ERR_WORKSPACE;
@@ -169,7 +181,7 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     else TEO_TRY(teo_patchify_f32_nchw(pixel_values, patches, n_frames, m->image, m->patch, m->kpad, stream));
     GemmEpilogue none;
     TEO_TRY(launch_gemm(h, patches, m->kpad, static_cast<const bf16*>(m->patch_w), m->kpad, patch_out, d, n_frames * np, d, m->kpad,
-                        none, nullptr, 0, stream, m->w_blocked));
+                        none, gws, gws_bytes, stream, m->w_blocked));
     TEO_TRY(teo_vit_assemble_preln(patch_out, m->cls, m->pos, m->pre_ln_w, m->pre_ln_b, hidden, n_frames, np, d, m->eps, stream));
     fill_cu_seqlens_kernel<<<(n_frames + 256) / 256, 256, 0, stream>>>(cu, n_frames, np + 1);
     TEO_LAUNCH_CHECK("fill_cu_seqlens_kernel");
@@ -180,24 +192,24 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
         TEO_TRY(teo_layernorm(hidden, L.ln1_w, L.ln1_b, ln_out, rows, d, m->eps, stream));
         GemmEpilogue e1;
         e1.bias = static_cast<const bf16*>(L.qkv_b);
-        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, nullptr, 0, stream, m->w_blocked));
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, gws, gws_bytes, stream, m->w_blocked));
         TEO_TRY(launch_flash_attention(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, m->heads, hd, scale,
                                        0, stream));
         GemmEpilogue e2;
         e2.bias = static_cast<const bf16*>(L.out_b);
         e2.residual = hidden;
         e2.ldr = d;
-        TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, nullptr, 0, stream, m->w_blocked));
+        TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, gws, gws_bytes, stream, m->w_blocked));
         TEO_TRY(teo_layernorm(hidden, L.ln2_w, L.ln2_b, ln_out, rows, d, m->eps, stream));
         GemmEpilogue e3;
         e3.bias = static_cast<const bf16*>(L.fc1_b);
         e3.act = m->act;
-        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.fc1_w), d, mlp, m->inter, rows, m->inter, d, e3, nullptr, 0, stream, m->w_blocked));
+        TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.fc1_w), d, mlp, m->inter, rows, m->inter, d, e3, gws, gws_bytes, stream, m->w_blocked));
         GemmEpilogue e4;
         e4.bias = static_cast<const bf16*>(L.fc2_b);
         e4.residual = hidden;
         e4.ldr = d;
-        TEO_TRY(launch_gemm(h, mlp, m->inter, static_cast<const bf16*>(L.fc2_w), m->inter, hidden, d, rows, d, m->inter, e4, nullptr, 0,
+        TEO_TRY(launch_gemm(h, mlp, m->inter, static_cast<const bf16*>(L.fc2_w), m->inter, hidden, d, rows, d, m->inter, e4, gws, gws_bytes,
                             stream, m->w_blocked));
         h->launches += 3;
     }
@@ -390,16 +402,15 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     TEO_TRY(teo_splice_embed(m->embed, nullptr, next_ids, w.x, n_seqs, hdim, stream));
     TEO_TRY(teo_rmsnorm(w.x, m->layer[0].in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
     h->launches += 2;
-    const float* P = reinterpret_cast<const float*>(w.gemm_ws);
     for (int l = 0; l < m->layers; ++l) {
         const teo_llama_layer& L = m->layer[l];
         const void* next_norm = (l + 1 < m->layers) ? m->layer[l + 1].in_norm : m->final_norm;
         if (fused) {
-            int sp = 1;
+            PartialInfo pi{};
             // qkv: GEMM partials → reduce + RoPE + KV-page write (position of the new token = tokens cached so far)
             TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.qkv_w), hdim, n_seqs, 3 * hdim, hdim, w.gemm_ws,
-                                         w.gemm_ws_bytes, &sp, stream, m->w_blocked));
-            TEO_TRY(launch_reduce_rope_kv_write(P, static_cast<long long>(n_seqs) * 3 * hdim, sp, w.qkv, static_cast<const int*>(seq_lens),
+                                         w.gemm_ws_bytes, &pi, stream, m->w_blocked));
+            TEO_TRY(launch_reduce_rope_kv_write(pi, w.qkv, static_cast<const int*>(seq_lens),
                                                 L.kv_pages, static_cast<const int*>(block_table), max_pages, n_seqs, m->heads, hd,
                                                 m->page_size, static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin),
                                                 stream));
@@ -408,17 +419,17 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
                                             max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
             // o_proj partials → reduce + residual + post-attention RMSNorm
             TEO_TRY(launch_gemm_partials(h, w.attn, hdim, static_cast<const bf16*>(L.o_w), hdim, n_seqs, hdim, hdim, w.gemm_ws, w.gemm_ws_bytes,
-                                         &sp, stream, m->w_blocked));
-            TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(L.post_norm),
+                                         &pi, stream, m->w_blocked));
+            TEO_TRY(launch_reduce_residual_rmsnorm(pi, w.x, static_cast<const bf16*>(L.post_norm),
                                                    w.norm_out, n_seqs, hdim, m->eps, stream));
             // gate/up partials → reduce + SwiGLU
             TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
-                                         w.gemm_ws_bytes, &sp, stream, m->w_blocked));
-            TEO_TRY(launch_reduce_swiglu(P, static_cast<long long>(n_seqs) * 2 * I, sp, w.act, n_seqs, I, stream));
+                                         w.gemm_ws_bytes, &pi, stream, m->w_blocked));
+            TEO_TRY(launch_reduce_swiglu(pi, w.act, n_seqs, I, stream));
             // down_proj partials → reduce + residual + the NEXT layer's input RMSNorm (or the final norm)
-            TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &sp,
+            TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &pi,
                                          stream, m->w_blocked));
-            TEO_TRY(launch_reduce_residual_rmsnorm(P, static_cast<long long>(n_seqs) * hdim, sp, w.x, static_cast<const bf16*>(next_norm),
+            TEO_TRY(launch_reduce_residual_rmsnorm(pi, w.x, static_cast<const bf16*>(next_norm),
                                                    w.norm_out, n_seqs, hdim, m->eps, stream));
             h->launches += 4;
         } else {
