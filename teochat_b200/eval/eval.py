@@ -4,7 +4,8 @@
 Offline there is no checkpoint, tokenizer or network, so ``model_path`` selects
 a synthetic ("random-init") model: ``"teochat-synthetic"`` / ``"teochat-synthetic-tiny"``,
 optionally ``?seed=N``.  Like the reference's builder (builder.py:33) the model name must contain
-``llava`` or ``teochat``.  Loading a real HF checkpoint directory is SURVEY.md §8(f) row 1.
+``llava`` or ``teochat``.  A directory path loads an HF-format checkpoint (merged, or a LoRA adapter over ``model_base``; a
+separate image-tower checkpoint directory may be given through ``cache_dir``) via teochat_b200.checkpoint.
 """
 from __future__ import annotations
 
@@ -27,15 +28,24 @@ def load_model(model_path, model_base=None, load_8bit=False, load_4bit=False, ca
     model_name = get_model_name_from_path(path)
     if "llava" not in model_name.lower() and "teochat" not in model_name.lower():
         raise ValueError(f"model name {model_name!r} must contain 'llava' or 'teochat' (builder.py:33)")
+    dev = torch.device(device if device is not None else "cuda:0")
     if os.path.isdir(path):
-        raise NotImplementedError("real-checkpoint loading is SURVEY.md §8(f) row 1 (next); use 'teochat-synthetic'")
+        # HF-format directory: merged checkpoint, or LoRA adapter over `model_base` (builder.py:33-112)
+        from .. import checkpoint as CK
+        cfg = CK.read_config(path)
+        sd = CK.load_state_dict(path, model_base if (model_base and os.path.isdir(str(model_base))) else None, tower_path=cache_dir)
+        weights = TeoWeights.from_state_dict(sd, cfg, dev)
+        del sd
+        model = TeoModel(cfg, weights, dev)
+        model.model.video_tower = None
+        return CK.load_tokenizer(model_base if (model_base and os.path.isdir(str(model_base))) else path, cfg.llama.vocab_size), model, \
+            TeoImageProcessor(cfg.vision.image_size)
     seed = 1234
     for kv in filter(None, query.split("&")):
         k, _, v = kv.partition("=")
         if k == "seed":
             seed = int(v)
     cfg = TeoConfig.tiny() if model_name.endswith("-tiny") else TeoConfig.full()
-    dev = torch.device(device if device is not None else "cuda:0")
     weights = TeoWeights.from_synthetic(cfg, seed, dev)
     model = TeoModel(cfg, weights, dev)
     model.model.video_tower = None                     # eval.py:31

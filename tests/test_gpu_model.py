@@ -278,3 +278,33 @@ def test_config1_full_size_vs_golden():
     assert n >= 1
     del model
     torch.cuda.empty_cache()
+
+
+def test_load_model_from_hf_directory(tmp_path, tiny):
+    """load_model on an HF-format directory (sharded safetensors + config.json) gives the same model as the
+    synthetic initialiser with the same seed (the oracle's checkpoint is that initialiser, bit for bit)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from oracle import weights as OW
+    from videollava.eval.eval import load_model
+    cfg, ref_model = tiny
+    sd = OW.make_state_dict(cfg, 1234, dtype=torch.bfloat16)
+    d = str(tmp_path / "teochat-tiny-hf")
+    os.makedirs(d)
+    l, v = cfg.llama, cfg.vision
+    with open(os.path.join(d, "config.json"), "w") as f:
+        json.dump({"hidden_size": l.hidden_size, "intermediate_size": l.intermediate_size, "num_hidden_layers": l.num_hidden_layers,
+                   "num_attention_heads": l.num_attention_heads, "vocab_size": l.vocab_size, "rms_norm_eps": l.rms_norm_eps,
+                   "max_position_embeddings": l.max_position_embeddings, "mm_projector_type": "mlp2x_gelu", "mm_vision_select_layer": -2,
+                   "vision_config": {"hidden_size": v.hidden_size, "intermediate_size": v.intermediate_size,
+                                     "num_hidden_layers": v.num_hidden_layers, "num_attention_heads": v.num_attention_heads,
+                                     "image_size": v.image_size, "patch_size": v.patch_size}}, f)
+    keys = sorted(sd)
+    save_file({k: sd[k].contiguous() for k in keys[::2]}, os.path.join(d, "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k].contiguous() for k in keys[1::2]}, os.path.join(d, "model-00002-of-00002.safetensors"))
+    tokenizer, model, processor = load_model(d, None, device=DEV)
+    for k, t in ref_model.w.t.items():
+        assert torch.equal(t, model.w.t[k]), k
+    assert processor.crop_size["height"] == v.image_size
