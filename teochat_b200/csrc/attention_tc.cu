@@ -1,0 +1,467 @@
+// Flash attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for the two dense attention
+// shapes of the hot path:
+//   ViT blocks      non-causal, 257 tokens per frame, head_dim 64   (HF CLIPAttention: softmax(q·s kᵀ) v)
+//   LLaMA prefill   causal, ragged batch of ~2.1k-token sequences, head_dim 128 (HF LlamaAttention, fp32 softmax)
+//
+// One CTA owns TWO 128-row query tiles of one (sequence, head) and walks the key/value blocks (128 keys) once:
+//   warp 0        TMA producer: Q tiles once, then K and V blocks into two mbarrier rings (128-byte swizzle;
+//                 head_dim 128 = two 64-column halves per tile)
+//   warp 1        MMA issuer (one thread): S_t = Q_t·Kᵀ (both operands K-major in shared memory) into TMEM,
+//                 O_t += P_t·V with P_t read from TMEM (A operand) and V MN-major straight from its TMA tile
+//   warp 2        TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_t overlays the first half of S_t)
+//   warps 4-7     softmax of tile 0, one thread per query row (= TMEM lane): row max, lazy rescale of O
+//   warps 8-11    softmax of tile 1        (only when the running max grows by > 2^8), exp2, bf16 P → TMEM
+// The two tiles ping-pong: while one tile's rows are in softmax, the tensor core runs the other tile's
+// P·V and next Q·Kᵀ.  tcgen05.mma retires in issue order, so the commit that publishes S_t(j+1) also
+// guarantees P_t(j)·V(j) is complete — the softmax warps may rescale O_t right after that wait.
+//
+// Numerics match flash_fwd_kernel (attention.cu): fp32 scores and statistics, P rounded to bf16 before P·V,
+// fp32 accumulation, one rounding of the output.  Algorithmic work 4·S²·d flop (half if causal).
+#include <cmath>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace teo {
+
+constexpr int FA_THREADS = 384;
+constexpr int FA_TILE_BYTES = 128 * 128;      // [128 rows][64 bf16] under the 128-byte swizzle
+constexpr float FA_RESCALE_LOG2 = 8.0f;       // O is rescaled only when the row max grew by more than 2^8
+
+template <int HD>
+struct FaCfg {
+    static constexpr int HALVES = HD / 64;
+    static constexpr int KV_TILE = HALVES * FA_TILE_BYTES;
+    static constexpr int Q_BYTES = 2 * KV_TILE;
+    static constexpr int STAGES = HD == 128 ? 2 : 4;
+    static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct FaArgs {
+    bf16* O;
+    long long ldo;
+    const int* cu_seqlens;
+    int n_heads, n_sh;          // n_sh = sequences × heads
+    int n_pairs;                // 256-row query groups per sequence (grid = n_pairs × n_sh)
+    int q_offset;               // the first q_offset rows of every sequence are not tiled here (ViT: CLS row)
+    int chunk;                  // (sequence, head) pairs scheduled together, heavy causal groups first
+    float scale_log2;
+};
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
+                const __grid_constant__ CUtensorMap tk32, const __grid_constant__ CUtensorMap tv32, const FaArgs g) {
+    using Cfg = FaCfg<HD>;
+    constexpr int HALVES = Cfg::HALVES, STAGES = Cfg::STAGES, KV_TILE = Cfg::KV_TILE;
+    constexpr uint32_t TM_S = 0, TM_O = 256;                    // TMEM column bases: S_t at 128·t, O_t at 256 + HD·t
+
+    // ---- work decode: chunks of (sequence, head) pairs; inside a chunk the heaviest (last) query groups first,
+    //      so the K/V of a chunk stay in L2 while the tail of one chunk overlaps the head of the next
+    int sh, pair;
+    {
+        const int per = g.chunk * g.n_pairs;
+        const int ch = blockIdx.x / per, rem = blockIdx.x - ch * per;
+        const int csz = min(g.chunk, g.n_sh - ch * g.chunk);
+        pair = g.n_pairs - 1 - rem / csz;
+        sh = ch * g.chunk + rem % csz;
+    }
+    const int seq = sh / g.n_heads, head = sh - seq * g.n_heads;
+    const int seq_start = g.cu_seqlens[seq];
+    const int seqlen = g.cu_seqlens[seq + 1] - seq_start;
+    const int nq = seqlen - g.q_offset;
+    const int m0 = pair * 256;
+    if (m0 >= nq) return;                                        // whole CTA, before any barrier / TMEM use
+    const int n_tiles = (nq - m0 > 128) ? 2 : 1;
+    const int nb_all = (seqlen + 127) >> 7;
+    int nb[2];
+    nb[0] = CAUSAL ? min(nb_all, (m0 >> 7) + 1) : nb_all;
+    nb[1] = n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (m0 >> 7) + 2) : nb_all);
+    const int nb_max = max(nb[0], nb[1]);
+    auto block_cols = [&](int j) { return min(128, (seqlen - (j << 7) + 31) & ~31); };
+
+    extern __shared__ uint8_t fa_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                         // [2 tiles][HALVES][128][64]
+    uint8_t* sK = sQ + Cfg::Q_BYTES;                            // [STAGES][HALVES][128][64]
+    uint8_t* sV = sK + STAGES * KV_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * KV_TILE);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = q_full + 1;
+    uint64_t* k_empty = k_full + STAGES;
+    uint64_t* v_full = k_empty + STAGES;
+    uint64_t* v_empty = v_full + STAGES;
+    uint64_t* s_full = v_empty + STAGES;                        // [2] S_t(j) complete (MMA → softmax)
+    uint64_t* p_full = s_full + 2;                              // [2] P_t(j) in TMEM, O_t rescaled (softmax → MMA)
+    uint64_t* o_full = p_full + 2;                              // [2] last P·V of tile t complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tq);
+        tma_prefetch_desc(&tk);
+        tma_prefetch_desc(&tv);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&s_full[t], 1);
+            mbar_init(&p_full[t], 128);
+            mbar_init(&o_full[t], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const int col0 = head * HD;
+            mbar_arrive_expect_tx(q_full, n_tiles * KV_TILE);
+            for (int t = 0; t < n_tiles; ++t)
+                for (int h = 0; h < HALVES; ++h)
+                    tma_load_2d(sQ + (t * HALVES + h) * FA_TILE_BYTES, &tq, q_full, col0 + 64 * h, seq_start + g.q_offset + m0 + 128 * t);
+            auto load_block = [&](uint8_t* dst, const CUtensorMap* big, const CUtensorMap* small, uint64_t* bar, int j) {
+                const int cols = block_cols(j), row = seq_start + (j << 7);
+                if (cols == 128) {
+                    mbar_arrive_expect_tx(bar, KV_TILE);
+                    for (int h = 0; h < HALVES; ++h) tma_load_2d(dst + h * FA_TILE_BYTES, big, bar, col0 + 64 * h, row);
+                } else {                                         // tail block: 32-row boxes, only the rows in use
+                    const int n32 = cols >> 5;
+                    mbar_arrive_expect_tx(bar, HALVES * n32 * 4096);
+                    for (int h = 0; h < HALVES; ++h)
+                        for (int i = 0; i < n32; ++i)
+                            tma_load_2d(dst + h * FA_TILE_BYTES + i * 4096, small, bar, col0 + 64 * h, row + 32 * i);
+                }
+            };
+            int s = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nb_max; ++j) {
+                mbar_wait(&k_empty[s], ph ^ 1);
+                load_block(sK + s * KV_TILE, &tk, &tk32, &k_full[s], j);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                load_block(sV + s * KV_TILE, &tv, &tv32, &v_full[s], j);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN_MAJOR;
+            auto issue_s = [&](int t, int stage, int cols) {           // S_t = Q_t · K(stage)ᵀ   [128 × cols]
+                const uint32_t idesc = umma_idesc_bf16(128, cols);
+#pragma unroll
+                for (int ks = 0; ks < HD / 16; ++ks) {
+                    const uint64_t a = umma_desc_k_sw128(smem_u32(sQ + (t * HALVES + ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
+                    const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
+                    umma_bf16(tmem_base + TM_S + 128 * t, a, b, idesc, ks > 0 ? 1u : 0u);
+                }
+            };
+            auto issue_pv = [&](int t, int stage, int cols, bool first) {   // O_t (+)= P_t · V(stage)   [128 × HD]
+                const uint32_t vbase = smem_u32(sV + stage * KV_TILE);
+                for (int ks = 0; ks < cols / 16; ++ks) {
+                    const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, FA_TILE_BYTES, 1024);
+                    umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + 128 * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                }
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            for (int t = 0; t < n_tiles; ++t) {
+                issue_s(t, 0, block_cols(0));
+                umma_commit(&s_full[t]);
+            }
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < nb_max; ++j) {
+                const int sv = j % STAGES;
+                const uint32_t phv = (j / STAGES) & 1;
+                const int sk = (j + 1) % STAGES;
+                const uint32_t phk = ((j + 1) / STAGES) & 1;
+                const int cols = block_cols(j);
+                bool v_ready = false;
+                for (int t = 0; t < n_tiles; ++t) {
+                    if (j >= nb[t]) continue;
+                    mbar_wait(&p_full[t], j & 1);
+                    if (!v_ready) {
+                        mbar_wait(&v_full[sv], phv);
+                        v_ready = true;
+                    }
+                    tc_fence_after();
+                    issue_pv(t, sv, cols, j == 0);
+                    if (j == nb[t] - 1) umma_commit(&o_full[t]);
+                    if (j + 1 < nb[t]) {
+                        mbar_wait(&k_full[sk], phk);
+                        tc_fence_after();
+                        issue_s(t, sk, block_cols(j + 1));
+                        umma_commit(&s_full[t]);
+                    }
+                }
+                umma_commit(&v_empty[sv]);
+                if (j + 1 < nb_max) umma_commit(&k_empty[sk]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
+        const int t = (warp - 4) >> 2;
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+        if (t < n_tiles) {
+            const int row = m0 + 128 * t + quad * 32 + lane;     // among the tiled rows of this sequence
+            const int qpos = g.q_offset + row;                   // position in the sequence (causal mask)
+            const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint32_t t_s = lane_base + TM_S + 128 * t;
+            const uint32_t t_o = lane_base + TM_O + HD * t;
+            float m_used = -INFINITY, l_run = 0.f;
+            const int nbt = nb[t];
+            for (int j = 0; j < nbt; ++j) {
+                const int cols = block_cols(j);
+                const int kv0 = j << 7;
+                const bool need_mask = (kv0 + cols > seqlen) || (CAUSAL && j == nbt - 1);
+                mbar_wait(&s_full[t], j & 1);
+                tc_fence_after();
+                // ---- pass 1: row max
+                float mx = -INFINITY;
+                for (int c = 0; c < cols; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_s + c, v);
+                    tmem_ld_wait();
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kv = kv0 + c + i;
+                            if (kv >= seqlen || (CAUSAL && kv > qpos)) v[i] = 0xFF800000u;   // -inf
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                }
+                // ---- lazy rescale of O (warp-uniform decision: tcgen05.ld/st are warp-collective)
+                if (j == 0) {
+                    m_used = mx;
+                } else {
+                    const bool grow = (mx - m_used) * g.scale_log2 > FA_RESCALE_LOG2;
+                    if (__any_sync(0xffffffffu, grow)) {
+                        const float m_new = fmaxf(m_used, mx);
+                        const float alpha = exp2f((m_used - m_new) * g.scale_log2);
+                        m_used = m_new;
+                        l_run *= alpha;
+#pragma unroll 1
+                        for (int c = 0; c < HD; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(t_o + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st_32x32(t_o + c, v);
+                        }
+                    }
+                }
+                const float neg_ms = -m_used * g.scale_log2;
+                // ---- pass 2: P = exp2(S·scale − m·scale) → bf16 pairs → TMEM (over the columns of S already consumed)
+                float rs = 0.f;
+                for (int c = 0; c < cols; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_s + c, v);
+                    tmem_ld_wait();
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kv = kv0 + c + i;
+                            if (kv >= seqlen || (CAUSAL && kv > qpos)) v[i] = 0xFF800000u;
+                        }
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = exp2f(fmaf(__uint_as_float(v[i]), g.scale_log2, neg_ms));
+                        const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), g.scale_log2, neg_ms));
+                        rs += p0 + p1;
+                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st_32x16(t_s + (c >> 1), pk);
+                }
+                l_run += rs;
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[t]);
+            }
+            // ---- epilogue: O / l → bf16 → global (rows of this sequence only)
+            mbar_wait(&o_full[t], 0);
+            tc_fence_after();
+            const bool row_ok = row < nq;
+            const float inv = 1.0f / l_run;
+            bf16* dst = g.O + static_cast<long long>(seq_start + qpos) * g.ldo + head * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_o + c, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        *reinterpret_cast<uint4*>(dst + c + i) =
+                            make_uint4(pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
+                                       pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
+                                       pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
+                                       pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// Rows the tiled kernel skips (q_offset > 0; the ViT CLS row): one warp per (sequence, head, row), online softmax
+// over all keys in chunks of 32 (lane = key), P rounded to bf16 like the tiled path, lanes own HD/32 output columns.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_rows_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk, const bf16* __restrict__ V,
+                 long long ldv, bf16* __restrict__ O, long long ldo, const int* __restrict__ cu_seqlens, int n_heads, int n_rows,
+                 int n_items, float scale_log2) {
+    constexpr int DPL = HD / 32;                                 // output columns per lane
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int lane = threadIdx.x & 31;
+    const int r = item % n_rows, sh = item / n_rows;
+    const int seq = sh / n_heads, head = sh - seq * n_heads;
+    const int seq_start = cu_seqlens[seq], seqlen = cu_seqlens[seq + 1] - seq_start;
+    if (r >= seqlen) return;
+    const bf16* qp = Q + static_cast<long long>(seq_start + r) * ldq + head * HD;
+    const bf16* kb = K + static_cast<long long>(seq_start) * ldk + head * HD;
+    const bf16* vb = V + static_cast<long long>(seq_start) * ldv + head * HD;
+    uint4 qv[HD / 8];
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) qv[c] = *reinterpret_cast<const uint4*>(qp + c * 8);
+    float m_run = -INFINITY, l_run = 0.f, acc[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < seqlen; k0 += 32) {
+        const int key = k0 + lane;
+        float s = -INFINITY;
+        if (key < seqlen) {
+            const bf16* kp = kb + static_cast<long long>(key) * ldk;
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kp + c * 8);
+                a += bf16_lo(kv.x) * bf16_lo(qv[c].x) + bf16_hi(kv.x) * bf16_hi(qv[c].x) + bf16_lo(kv.y) * bf16_lo(qv[c].y) +
+                     bf16_hi(kv.y) * bf16_hi(qv[c].y) + bf16_lo(kv.z) * bf16_lo(qv[c].z) + bf16_hi(kv.z) * bf16_hi(qv[c].z) +
+                     bf16_lo(kv.w) * bf16_lo(qv[c].w) + bf16_hi(kv.w) * bf16_hi(qv[c].w);
+            }
+            s = a;
+        }
+        const float m_new = fmaxf(m_run, warp_max(s));           // k0 < seqlen ⇒ at least lane 0 is finite
+        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * scale_log2);
+        const float p = exp2f((s - m_new) * scale_log2);        // 0 for masked lanes
+        l_run = l_run * alpha + warp_sum(p);
+        m_run = m_new;
+        const float pb = __bfloat162float(__float2bfloat16_rn(p));
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) acc[i] *= alpha;
+        const int n = min(32, seqlen - k0);
+        for (int kk = 0; kk < n; ++kk) {
+            const float pk = __shfl_sync(0xffffffffu, pb, kk);
+            const bf16* vp = vb + static_cast<long long>(k0 + kk) * ldv + lane * DPL;
+            if (DPL == 2) {
+                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vp);
+                acc[0] += pk * bf16_lo(vv);
+                acc[1] += pk * bf16_hi(vv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) acc[i] += pk * __bfloat162float(vp[i]);
+            }
+        }
+    }
+    const float inv = 1.0f / l_run;
+    bf16* op = O + static_cast<long long>(seq_start + r) * ldo + head * HD + lane * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) op[i] = __float2bfloat16_rn(acc[i] * inv);
+}
+
+template <int HD, bool CAUSAL>
+static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
+                             const int* cu, int n_seqs, int max_seqlen, int total_tokens, int n_heads, float scale, int q_offset,
+                             cudaStream_t stream) {
+    using Cfg = FaCfg<HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TEO_CUDA(cudaFuncSetAttribute(flash_tc_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    const CUtensorMap *tq, *tk, *tv, *tk32, *tv32;
+    const uint64_t cols = static_cast<uint64_t>(n_heads) * HD;
+    TEO_TRY(get_tmap_bf16(h, q, total_tokens, cols, ldq, 128, &tq));
+    TEO_TRY(get_tmap_bf16(h, k, total_tokens, cols, ldk, 128, &tk));
+    TEO_TRY(get_tmap_bf16(h, v, total_tokens, cols, ldv, 128, &tv));
+    TEO_TRY(get_tmap_bf16(h, k, total_tokens, cols, ldk, 32, &tk32));
+    TEO_TRY(get_tmap_bf16(h, v, total_tokens, cols, ldv, 32, &tv32));
+    FaArgs g{};
+    g.O = out;
+    g.ldo = ldo;
+    g.cu_seqlens = cu;
+    g.n_heads = n_heads;
+    g.n_sh = n_seqs * n_heads;
+    g.n_pairs = (max_seqlen - q_offset + 255) / 256;
+    g.q_offset = q_offset;
+    g.chunk = std::min(g.n_sh, 64);          // ≈ 64 × (K+V of one head) stays well inside the 126 MB L2
+    g.scale_log2 = scale * 1.4426950408889634f;
+    const int n_chunks = (g.n_sh + g.chunk - 1) / g.chunk;
+    (void)n_chunks;
+    const long long grid = static_cast<long long>(g.n_sh) * g.n_pairs;
+    flash_tc_kernel<HD, CAUSAL><<<static_cast<unsigned>(grid), FA_THREADS, Cfg::SMEM, stream>>>(*tq, *tk, *tv, *tk32, *tv32, g);
+    TEO_LAUNCH_CHECK("flash_tc_kernel");
+    h->launches++;
+    if (q_offset > 0) {
+        const int items = g.n_sh * q_offset;
+        attn_rows_kernel<HD><<<(items + 3) / 4, 128, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, cu, n_heads, q_offset, items, g.scale_log2);
+        TEO_LAUNCH_CHECK("attn_rows_kernel");
+        h->launches++;
+    }
+    return TEO_OK;
+}
+
+// q_offset rows at the start of every sequence go through attn_rows_kernel instead of a (mostly empty) 128-row tile:
+// the ViT passes 1, so that its 257 tokens are the CLS row + exactly two query tiles.
+int launch_flash_attention_tc(teo_handle* h, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
+                              const int* cu_seqlens, int n_seqs, int max_seqlen, int total_tokens, int n_heads, int head_dim,
+                              float scale, int causal, int q_offset, cudaStream_t stream) {
+    TEO_CHECK_ARG(h && q && k && v && out && cu_seqlens, "flash_attention_tc: null pointer");
+    TEO_CHECK_ARG(n_seqs > 0 && max_seqlen > 0 && n_heads > 0 && total_tokens > 0, "flash_attention_tc: bad sizes");
+    TEO_CHECK_ARG(q_offset >= 0 && q_offset < max_seqlen && !(causal && q_offset), "flash_attention_tc: bad q_offset %d", q_offset);
+    TEO_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "flash_attention_tc: output rows must be 16-byte aligned");
+    if (head_dim == 64 && !causal)
+        return launch_flash_tc_t<64, false>(h, q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, n_seqs, max_seqlen, total_tokens, n_heads, scale, q_offset, stream);
+    if (head_dim == 64 && causal)
+        return launch_flash_tc_t<64, true>(h, q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, n_seqs, max_seqlen, total_tokens, n_heads, scale, q_offset, stream);
+    if (head_dim == 128 && !causal)
+        return launch_flash_tc_t<128, false>(h, q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, n_seqs, max_seqlen, total_tokens, n_heads, scale, q_offset, stream);
+    if (head_dim == 128 && causal)
+        return launch_flash_tc_t<128, true>(h, q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, n_seqs, max_seqlen, total_tokens, n_heads, scale, q_offset, stream);
+    set_error("flash_attention_tc: head_dim %d unsupported (64 or 128)", head_dim);
+    return TEO_ERR_UNSUPPORTED;
+}
+
+}  // namespace teo
+
+extern "C" int teo_flash_attention_tc(teo_handle* h, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                      int ldo, const void* cu_seqlens, int n_seqs, int max_seqlen, int total_tokens, int n_heads,
+                                      int head_dim, float scale, int causal, int q_offset, void* stream) {
+    return teo::launch_flash_attention_tc(h, static_cast<const teo::bf16*>(q), ldq, static_cast<const teo::bf16*>(k), ldk,
+                                          static_cast<const teo::bf16*>(v), ldv, static_cast<teo::bf16*>(out), ldo,
+                                          static_cast<const int*>(cu_seqlens), n_seqs, max_seqlen, total_tokens, n_heads, head_dim, scale,
+                                          causal, q_offset, static_cast<cudaStream_t>(stream));
+}

@@ -34,6 +34,17 @@ void set_error(const char* fmt, ...) {
 int launch_flash_attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
                            const int* cu_seqlens, int n_seqs, int max_seqlen, int n_heads, int head_dim, float scale,
                            int causal, cudaStream_t stream);
+int launch_flash_attention_tc(teo_handle* h, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
+                              const int* cu_seqlens, int n_seqs, int max_seqlen, int total_tokens, int n_heads, int head_dim,
+                              float scale, int causal, int q_offset, cudaStream_t stream);
+// TEO_FLASH=mma selects the mma.sync kernels of attention.cu (A/B measurements); default is the tcgen05 path.
+static bool flash_use_tc() {
+    static const bool tc = [] {
+        const char* e = getenv("TEO_FLASH");
+        return !(e && e[0] == 'm');
+    }();
+    return tc;
+}
 int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* kv_pages, const int* block_table, int max_pages,
                             const int* seq_lens, int len_bias, bf16* out, int n_seqs, int n_heads, int head_dim, int page_size,
                             int max_seq_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -193,8 +204,12 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
         GemmEpilogue e1;
         e1.bias = static_cast<const bf16*>(L.qkv_b);
         TEO_TRY(launch_gemm(h, ln_out, d, static_cast<const bf16*>(L.qkv_w), d, qkv, 3 * d, rows, 3 * d, d, e1, gws, gws_bytes, stream, m->w_blocked));
-        TEO_TRY(launch_flash_attention(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, m->heads, hd, scale,
-                                       0, stream));
+        if (flash_use_tc() && (hd == 64 || hd == 128))      // CLS row separately: 257 tokens = 1 + two 128-row query tiles
+            TEO_TRY(launch_flash_attention_tc(h, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, rows,
+                                              m->heads, hd, scale, 0, (np % 128 == 0) ? 1 : 0, stream));
+        else
+            TEO_TRY(launch_flash_attention(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, m->heads, hd,
+                                           scale, 0, stream));
         GemmEpilogue e2;
         e2.bias = static_cast<const bf16*>(L.out_b);
         e2.residual = hidden;
@@ -323,8 +338,13 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
         TEO_TRY(launch_rope_kv_write(w.qkv, static_cast<const int*>(positions), static_cast<const int*>(seq_ids), L.kv_pages,
                                      static_cast<const int*>(block_table), max_pages, tokens, m->heads, hd, m->page_size,
                                      static_cast<const float*>(m->rope_cos), static_cast<const float*>(m->rope_sin), stream));
-        TEO_TRY(launch_flash_attention(w.qkv, 3 * hdim, w.qkv + hdim, 3 * hdim, w.qkv + 2 * hdim, 3 * hdim, w.attn, hdim,
-                                       static_cast<const int*>(cu_seqlens), n_seqs, max_seqlen, m->heads, hd, scale, 1, stream));
+        if (flash_use_tc() && (hd == 64 || hd == 128))
+            TEO_TRY(launch_flash_attention_tc(h, w.qkv, 3 * hdim, w.qkv + hdim, 3 * hdim, w.qkv + 2 * hdim, 3 * hdim, w.attn, hdim,
+                                              static_cast<const int*>(cu_seqlens), n_seqs, max_seqlen, tokens, m->heads, hd, scale, 1, 0,
+                                              stream));
+        else
+            TEO_TRY(launch_flash_attention(w.qkv, 3 * hdim, w.qkv + hdim, 3 * hdim, w.qkv + 2 * hdim, 3 * hdim, w.attn, hdim,
+                                           static_cast<const int*>(cu_seqlens), n_seqs, max_seqlen, m->heads, hd, scale, 1, stream));
         GemmEpilogue res;
         res.residual = x;
         res.ldr = hdim;

@@ -70,6 +70,7 @@ _SIGS = {
     "teo_layernorm": (i, [vp, vp, vp, vp, i, i, f, vp]),
     "teo_vit_drop_cls": (i, [vp, vp, i, i, i, vp]),
     "teo_flash_attention": (i, [vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, f, i, vp]),
+    "teo_flash_attention_tc": (i, [vp, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, f, i, i, vp]),
     "teo_rope_kv_write": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
     "teo_decode_attention_workspace_bytes": (sz, [i, i, i, i]),
     "teo_decode_attention": (i, [vp, i, vp, vp, i, vp, vp, i, i, i, i, i, f, vp, sz, vp]),

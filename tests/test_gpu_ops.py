@@ -256,6 +256,57 @@ def test_flash_attention(teo, hd, H, lens, causal):
         o += n
 
 
+@pytest.mark.parametrize("hd,H,lens,causal,q_offset", [
+    (64, 16, [257, 257, 257], False, 1),         # ViT block shape: CLS row by the row kernel + two query tiles
+    (64, 16, [257, 257], False, 0),              # same tokens, everything tiled (third tile holds one row)
+    (64, 2, [17, 17], False, 1),                 # tiny ViT
+    (64, 3, [1, 33, 128, 129, 300, 513], False, 0),
+    (64, 2, [100, 256, 700], True, 0),
+    (128, 4, [580], True, 0),                    # config (1) prefill shape
+    (128, 2, [1, 63, 64, 65, 130, 300], True, 0),    # ragged batch with edge lengths
+    (128, 2, [127, 128, 129, 255, 256, 257, 385], True, 0),   # tile / block boundaries
+    (128, 32, [2151, 2130], True, 0),            # bench prefill shape (two sequences, all heads)
+    (128, 2, [200, 31, 1000], False, 0),
+])
+def test_flash_attention_tc(teo, hd, H, lens, causal, q_offset):
+    """tcgen05 flash attention (the path teo_vit_encode / teo_llama_prefill take) vs the fp32 restatement."""
+    lib, h = teo
+    T = sum(lens)
+    d = H * hd
+    qkv = bf(rnd(T, 3 * d, seed=13))
+    qkv[:, :d] *= 3.0                           # wider score range: exercises the running-max / lazy-rescale path
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    out = torch.full((T, d), float("nan"), dtype=torch.bfloat16, device=DEV)
+    scale = hd ** -0.5
+    L.check(lib.teo_flash_attention_tc(h, qkv.data_ptr(), 3 * d, qkv[:, d:].data_ptr(), 3 * d, qkv[:, 2 * d:].data_ptr(), 3 * d,
+                                       out.data_ptr(), d, cu.data_ptr(), len(lens), max(lens), T, H, hd, scale, int(causal), q_offset,
+                                       stream()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any(), "rows left unwritten"
+    o = 0
+    for n in lens:
+        q, k, v = [qkv[o:o + n, i * d:(i + 1) * d].float().view(n, H, hd) for i in range(3)]
+        ref = _attn_ref(q, k, v, scale, causal).reshape(n, d)
+        err = (out[o:o + n].float() - ref).abs().max().item()
+        assert err <= 1.5e-2 * ref.abs().max().item(), (n, err)     # bf16 P and bf16 output rounding
+        o += n
+
+
+def test_flash_attention_tc_matches_mma_path(teo):
+    """The two flash kernels agree to bf16 rounding on the ViT shape (same rounding points)."""
+    lib, h = teo
+    hd, H, lens = 64, 16, [257] * 8
+    T, d = sum(lens), H * hd
+    qkv = bf(rnd(T, 3 * d, seed=14))
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    a = torch.empty(T, d, dtype=torch.bfloat16, device=DEV)
+    b = torch.empty_like(a)
+    args = (qkv.data_ptr(), 3 * d, qkv[:, d:].data_ptr(), 3 * d, qkv[:, 2 * d:].data_ptr(), 3 * d)
+    L.check(lib.teo_flash_attention(*args, a.data_ptr(), d, cu.data_ptr(), len(lens), 257, H, hd, hd ** -0.5, 0, stream()))
+    L.check(lib.teo_flash_attention_tc(h, *args, b.data_ptr(), d, cu.data_ptr(), len(lens), 257, T, H, hd, hd ** -0.5, 0, 1, stream()))
+    assert (a.float() - b.float()).abs().max().item() <= 2 ** -7 * a.float().abs().max().item()
+
+
 @pytest.mark.parametrize("hd,ps,H,lens", [
     (128, 64, 32, [2151, 580, 64, 65, 1, 4000]),      # forces several KV splits
     (128, 64, 4, [300] * 40),                         # many sequences → single split
