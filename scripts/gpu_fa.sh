@@ -2,7 +2,7 @@
 # tcgen05 flash attention bring-up: operand-form probes, parity tests (one process per case group), kernel timing
 mkdir -p gpurun_out
 P=tools/_build/probe_umma
-{
+[ "$1" == "probe" ] && {
   echo "== probes"
   for args in "0 64 16384 1024 2048 0" "0 128 16384 1024 2048 0" "1 64 16384 1024 2048 0" "1 128 16384 1024 2048 0" \
               "0 128 1024 16384 2048 0" "0 64 1024 16384 2048 0" "1 64 16384 1024 2048 1" "0 64 16384 1024 32 0" "0 64 1024 1024 2048 0"; do

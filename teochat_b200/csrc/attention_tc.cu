@@ -32,9 +32,10 @@ template <int HD>
 struct FaCfg {
     static constexpr int HALVES = HD / 64;
     static constexpr int KV_TILE = HALVES * FA_TILE_BYTES;
-    static constexpr int Q_BYTES = 2 * KV_TILE;
+    static constexpr int Q_SET = 2 * KV_TILE;                   // both query tiles of one work item
+    static constexpr int Q_SETS = HD == 128 ? 1 : 2;            // head_dim 64: the next item's Q loads under the current one
     static constexpr int STAGES = HD == 128 ? 2 : 4;
-    static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM = Q_SETS * Q_SET + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct FaArgs {
@@ -42,52 +43,67 @@ struct FaArgs {
     long long ldo;
     const int* cu_seqlens;
     int n_heads, n_sh;          // n_sh = sequences × heads
-    int n_pairs;                // 256-row query groups per sequence (grid = n_pairs × n_sh)
+    int n_pairs;                // 256-row query groups per sequence; work items = n_pairs × n_sh
     int q_offset;               // the first q_offset rows of every sequence are not tiled here (ViT: CLS row)
     int chunk;                  // (sequence, head) pairs scheduled together, heavy causal groups first
     float scale_log2;
 };
+
+// One work item = two adjacent 128-row query tiles of one (sequence, head).  Items are ordered in chunks of
+// (sequence, head) pairs; inside a chunk the heaviest (last) query groups come first, so the K/V of a chunk stay
+// in L2 while the persistent CTAs (item i → CTA i mod grid) each get a similar mix of heavy and light items.
+struct FaItem {
+    int head, seq_start, seqlen, nq, m0, n_tiles, nb[2], nb_max;
+    bool valid;
+};
+template <bool CAUSAL>
+__device__ __forceinline__ FaItem fa_decode(const FaArgs& g, int idx) {
+    FaItem it;
+    const int per = g.chunk * g.n_pairs;
+    const int ch = idx / per, rem = idx - ch * per;
+    const int csz = min(g.chunk, g.n_sh - ch * g.chunk);
+    const int pair = g.n_pairs - 1 - rem / csz;
+    const int sh = ch * g.chunk + rem % csz;
+    const int seq = sh / g.n_heads;
+    it.head = sh - seq * g.n_heads;
+    it.seq_start = g.cu_seqlens[seq];
+    it.seqlen = g.cu_seqlens[seq + 1] - it.seq_start;
+    it.nq = it.seqlen - g.q_offset;
+    it.m0 = pair * 256;
+    it.valid = it.m0 < it.nq;
+    it.n_tiles = (it.nq - it.m0 > 128) ? 2 : 1;
+    const int nb_all = (it.seqlen + 127) >> 7;
+    it.nb[0] = CAUSAL ? min(nb_all, (it.m0 >> 7) + 1) : nb_all;
+    it.nb[1] = it.n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (it.m0 >> 7) + 2) : nb_all);
+    it.nb_max = max(it.nb[0], it.nb[1]);
+    return it;
+}
+__device__ __forceinline__ int fa_block_cols(int seqlen, int j) { return min(128, (seqlen - (j << 7) + 31) & ~31); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                 const __grid_constant__ CUtensorMap tk32, const __grid_constant__ CUtensorMap tv32, const FaArgs g) {
     using Cfg = FaCfg<HD>;
-    constexpr int HALVES = Cfg::HALVES, STAGES = Cfg::STAGES, KV_TILE = Cfg::KV_TILE;
+    constexpr int HALVES = Cfg::HALVES, STAGES = Cfg::STAGES, KV_TILE = Cfg::KV_TILE, Q_SETS = Cfg::Q_SETS;
     constexpr uint32_t TM_S = 0, TM_O = 256;                    // TMEM column bases: S_t at 128·t, O_t at 256 + HD·t
-
-    // ---- work decode: chunks of (sequence, head) pairs; inside a chunk the heaviest (last) query groups first,
-    //      so the K/V of a chunk stay in L2 while the tail of one chunk overlaps the head of the next
-    int sh, pair;
-    {
-        const int per = g.chunk * g.n_pairs;
-        const int ch = blockIdx.x / per, rem = blockIdx.x - ch * per;
-        const int csz = min(g.chunk, g.n_sh - ch * g.chunk);
-        pair = g.n_pairs - 1 - rem / csz;
-        sh = ch * g.chunk + rem % csz;
-    }
-    const int seq = sh / g.n_heads, head = sh - seq * g.n_heads;
-    const int seq_start = g.cu_seqlens[seq];
-    const int seqlen = g.cu_seqlens[seq + 1] - seq_start;
-    const int nq = seqlen - g.q_offset;
-    const int m0 = pair * 256;
-    if (m0 >= nq) return;                                        // whole CTA, before any barrier / TMEM use
-    const int n_tiles = (nq - m0 > 128) ? 2 : 1;
-    const int nb_all = (seqlen + 127) >> 7;
-    int nb[2];
-    nb[0] = CAUSAL ? min(nb_all, (m0 >> 7) + 1) : nb_all;
-    nb[1] = n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (m0 >> 7) + 2) : nb_all);
-    const int nb_max = max(nb[0], nb[1]);
-    auto block_cols = [&](int j) { return min(128, (seqlen - (j << 7) + 31) & ~31); };
+    const int n_items = g.n_sh * g.n_pairs;
 
     extern __shared__ uint8_t fa_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                         // [2 tiles][HALVES][128][64]
-    uint8_t* sK = sQ + Cfg::Q_BYTES;                            // [STAGES][HALVES][128][64]
+    uint8_t* sQ = smem;                                         // [Q_SETS][2 tiles][HALVES][128][64]
+    uint8_t* sK = sQ + Q_SETS * Cfg::Q_SET;                     // [STAGES][HALVES][128][64]
     uint8_t* sV = sK + STAGES * KV_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * KV_TILE);
-    uint64_t* q_full = bars;
-    uint64_t* k_full = q_full + 1;
+    uint64_t* q_full = bars;                                    // [Q_SETS]
+    uint64_t* q_empty = q_full + Q_SETS;
+    uint64_t* k_full = q_empty + Q_SETS;
     uint64_t* k_empty = k_full + STAGES;
     uint64_t* v_full = k_empty + STAGES;
     uint64_t* v_empty = v_full + STAGES;
@@ -103,7 +119,10 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         tma_prefetch_desc(&tv);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(q_full, 1);
+        for (int s = 0; s < Q_SETS; ++s) {
+            mbar_init(&q_full[s], 1);
+            mbar_init(&q_empty[s], 1);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&k_full[s], 1);
             mbar_init(&k_empty[s], 1);
@@ -126,32 +145,40 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            const int col0 = head * HD;
-            mbar_arrive_expect_tx(q_full, n_tiles * KV_TILE);
-            for (int t = 0; t < n_tiles; ++t)
-                for (int h = 0; h < HALVES; ++h)
-                    tma_load_2d(sQ + (t * HALVES + h) * FA_TILE_BYTES, &tq, q_full, col0 + 64 * h, seq_start + g.q_offset + m0 + 128 * t);
-            auto load_block = [&](uint8_t* dst, const CUtensorMap* big, const CUtensorMap* small, uint64_t* bar, int j) {
-                const int cols = block_cols(j), row = seq_start + (j << 7);
-                if (cols == 128) {
-                    mbar_arrive_expect_tx(bar, KV_TILE);
-                    for (int h = 0; h < HALVES; ++h) tma_load_2d(dst + h * FA_TILE_BYTES, big, bar, col0 + 64 * h, row);
-                } else {                                         // tail block: 32-row boxes, only the rows in use
-                    const int n32 = cols >> 5;
-                    mbar_arrive_expect_tx(bar, HALVES * n32 * 4096);
+            uint32_t kv_cnt = 0, q_cnt = 0;
+            for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+                const FaItem it = fa_decode<CAUSAL>(g, idx);
+                if (!it.valid) continue;
+                const int col0 = it.head * HD;
+                const int qs = q_cnt % Q_SETS;
+                mbar_wait(&q_empty[qs], ((q_cnt / Q_SETS) & 1) ^ 1);
+                mbar_arrive_expect_tx(&q_full[qs], it.n_tiles * KV_TILE);
+                for (int t = 0; t < it.n_tiles; ++t)
                     for (int h = 0; h < HALVES; ++h)
-                        for (int i = 0; i < n32; ++i)
-                            tma_load_2d(dst + h * FA_TILE_BYTES + i * 4096, small, bar, col0 + 64 * h, row + 32 * i);
+                        tma_load_2d(sQ + qs * Cfg::Q_SET + (t * HALVES + h) * FA_TILE_BYTES, &tq, &q_full[qs], col0 + 64 * h,
+                                    it.seq_start + g.q_offset + it.m0 + 128 * t);
+                ++q_cnt;
+                auto load_block = [&](uint8_t* dst, const CUtensorMap* big, const CUtensorMap* small, uint64_t* bar, int j) {
+                    const int cols = fa_block_cols(it.seqlen, j), row = it.seq_start + (j << 7);
+                    if (cols == 128) {
+                        mbar_arrive_expect_tx(bar, KV_TILE);
+                        for (int h = 0; h < HALVES; ++h) tma_load_2d(dst + h * FA_TILE_BYTES, big, bar, col0 + 64 * h, row);
+                    } else {                                     // tail block: 32-row boxes, only the rows in use
+                        const int n32 = cols >> 5;
+                        mbar_arrive_expect_tx(bar, HALVES * n32 * 4096);
+                        for (int h = 0; h < HALVES; ++h)
+                            for (int i = 0; i < n32; ++i)
+                                tma_load_2d(dst + h * FA_TILE_BYTES + i * 4096, small, bar, col0 + 64 * h, row + 32 * i);
+                    }
+                };
+                for (int j = 0; j < it.nb_max; ++j, ++kv_cnt) {
+                    const int s = kv_cnt % STAGES;
+                    const uint32_t ph = (kv_cnt / STAGES) & 1;
+                    mbar_wait(&k_empty[s], ph ^ 1);
+                    load_block(sK + s * KV_TILE, &tk, &tk32, &k_full[s], j);
+                    mbar_wait(&v_empty[s], ph ^ 1);
+                    load_block(sV + s * KV_TILE, &tv, &tv32, &v_full[s], j);
                 }
-            };
-            int s = 0;
-            uint32_t ph = 0;
-            for (int j = 0; j < nb_max; ++j) {
-                mbar_wait(&k_empty[s], ph ^ 1);
-                load_block(sK + s * KV_TILE, &tk, &tk32, &k_full[s], j);
-                mbar_wait(&v_empty[s], ph ^ 1);
-                load_block(sV + s * KV_TILE, &tv, &tv32, &v_full[s], j);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
         __syncwarp();
@@ -159,56 +186,66 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN_MAJOR;
-            auto issue_s = [&](int t, int stage, int cols) {           // S_t = Q_t · K(stage)ᵀ   [128 × cols]
-                const uint32_t idesc = umma_idesc_bf16(128, cols);
+            uint32_t kv_cnt = 0, q_cnt = 0, n_t[2] = {0, 0};
+            for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+                const FaItem it = fa_decode<CAUSAL>(g, idx);
+                if (!it.valid) continue;
+                const int qs = q_cnt % Q_SETS;
+                const uint8_t* sQi = sQ + qs * Cfg::Q_SET;
+                auto issue_s = [&](int t, int stage, int cols) {           // S_t = Q_t · K(stage)ᵀ   [128 × cols]
+                    const uint32_t idesc = umma_idesc_bf16(128, cols);
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks) {
-                    const uint64_t a = umma_desc_k_sw128(smem_u32(sQ + (t * HALVES + ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
-                    const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
-                    umma_bf16(tmem_base + TM_S + 128 * t, a, b, idesc, ks > 0 ? 1u : 0u);
-                }
-            };
-            auto issue_pv = [&](int t, int stage, int cols, bool first) {   // O_t (+)= P_t · V(stage)   [128 × HD]
-                const uint32_t vbase = smem_u32(sV + stage * KV_TILE);
-                for (int ks = 0; ks < cols / 16; ++ks) {
-                    const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, FA_TILE_BYTES, 1024);
-                    umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + 128 * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
-                }
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            for (int t = 0; t < n_tiles; ++t) {
-                issue_s(t, 0, block_cols(0));
-                umma_commit(&s_full[t]);
-            }
-            umma_commit(&k_empty[0]);
-            for (int j = 0; j < nb_max; ++j) {
-                const int sv = j % STAGES;
-                const uint32_t phv = (j / STAGES) & 1;
-                const int sk = (j + 1) % STAGES;
-                const uint32_t phk = ((j + 1) / STAGES) & 1;
-                const int cols = block_cols(j);
-                bool v_ready = false;
-                for (int t = 0; t < n_tiles; ++t) {
-                    if (j >= nb[t]) continue;
-                    mbar_wait(&p_full[t], j & 1);
-                    if (!v_ready) {
-                        mbar_wait(&v_full[sv], phv);
-                        v_ready = true;
+                    for (int ks = 0; ks < HD / 16; ++ks) {
+                        const uint64_t a = umma_desc_k_sw128(smem_u32(sQi + (t * HALVES + ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
+                        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
+                        umma_bf16(tmem_base + TM_S + 128 * t, a, b, idesc, ks > 0 ? 1u : 0u);
                     }
-                    tc_fence_after();
-                    issue_pv(t, sv, cols, j == 0);
-                    if (j == nb[t] - 1) umma_commit(&o_full[t]);
-                    if (j + 1 < nb[t]) {
-                        mbar_wait(&k_full[sk], phk);
+                };
+                auto issue_pv = [&](int t, int stage, int cols, bool first) {   // O_t (+)= P_t · V(stage)   [128 × HD]
+                    const uint32_t vbase = smem_u32(sV + stage * KV_TILE);
+                    for (int ks = 0; ks < cols / 16; ++ks) {
+                        const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, FA_TILE_BYTES, 1024);
+                        umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + 128 * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                    }
+                };
+                mbar_wait(&q_full[qs], (q_cnt / Q_SETS) & 1);
+                mbar_wait(&k_full[kv_cnt % STAGES], (kv_cnt / STAGES) & 1);
+                tc_fence_after();
+                for (int t = 0; t < it.n_tiles; ++t) {
+                    issue_s(t, kv_cnt % STAGES, fa_block_cols(it.seqlen, 0));
+                    umma_commit(&s_full[t]);
+                }
+                umma_commit(&k_empty[kv_cnt % STAGES]);
+                if (it.nb_max == 1) umma_commit(&q_empty[qs]);
+                for (int j = 0; j < it.nb_max; ++j) {
+                    const uint32_t cv = kv_cnt + j, ck = cv + 1;
+                    const int sv = cv % STAGES, sk = ck % STAGES;
+                    const int cols = fa_block_cols(it.seqlen, j);
+                    bool v_ready = false;
+                    for (int t = 0; t < it.n_tiles; ++t) {
+                        if (j >= it.nb[t]) continue;
+                        mbar_wait(&p_full[t], n_t[t] & 1);
+                        ++n_t[t];
+                        if (!v_ready) {
+                            mbar_wait(&v_full[sv], (cv / STAGES) & 1);
+                            v_ready = true;
+                        }
                         tc_fence_after();
-                        issue_s(t, sk, block_cols(j + 1));
-                        umma_commit(&s_full[t]);
+                        issue_pv(t, sv, cols, j == 0);
+                        if (j == it.nb[t] - 1) umma_commit(&o_full[t]);
+                        if (j + 1 < it.nb[t]) {
+                            mbar_wait(&k_full[sk], (ck / STAGES) & 1);
+                            tc_fence_after();
+                            issue_s(t, sk, fa_block_cols(it.seqlen, j + 1));
+                            umma_commit(&s_full[t]);
+                        }
                     }
+                    umma_commit(&v_empty[sv]);
+                    if (j + 1 < it.nb_max) umma_commit(&k_empty[sk]);
+                    if (j + 2 == it.nb_max) umma_commit(&q_empty[qs]);     // the item's last Q·Kᵀ has been issued
                 }
-                umma_commit(&v_empty[sv]);
-                if (j + 1 < nb_max) umma_commit(&k_empty[sk]);
+                kv_cnt += it.nb_max;
+                ++q_cnt;
             }
         }
         __syncwarp();
@@ -216,36 +253,55 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
         const int t = (warp - 4) >> 2;
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
-        if (t < n_tiles) {
-            const int row = m0 + 128 * t + quad * 32 + lane;     // among the tiled rows of this sequence
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t t_s = lane_base + TM_S + 128 * t;
+        const uint32_t t_o = lane_base + TM_O + HD * t;
+        uint32_t n_blk = 0, n_out = 0;                           // phase counters of s_full[t] / o_full[t]
+        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+            const FaItem it = fa_decode<CAUSAL>(g, idx);
+            if (!it.valid || t >= it.n_tiles) continue;
+            const int seqlen = it.seqlen;
+            const int row = it.m0 + 128 * t + quad * 32 + lane;  // among the tiled rows of this sequence
             const int qpos = g.q_offset + row;                   // position in the sequence (causal mask)
-            const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-            const uint32_t t_s = lane_base + TM_S + 128 * t;
-            const uint32_t t_o = lane_base + TM_O + HD * t;
             float m_used = -INFINITY, l_run = 0.f;
-            const int nbt = nb[t];
-            for (int j = 0; j < nbt; ++j) {
-                const int cols = block_cols(j);
+            const int nbt = it.nb[t];
+            for (int j = 0; j < nbt; ++j, ++n_blk) {
+                const int cols = fa_block_cols(seqlen, j);
                 const int kv0 = j << 7;
                 const bool need_mask = (kv0 + cols > seqlen) || (CAUSAL && j == nbt - 1);
-                mbar_wait(&s_full[t], j & 1);
+                mbar_wait(&s_full[t], n_blk & 1);
                 tc_fence_after();
-                // ---- pass 1: row max
-                float mx = -INFINITY;
-                for (int c = 0; c < cols; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_s + c, v);
-                    tmem_ld_wait();
-                    if (need_mask) {
+                // ---- the whole score row of this block → registers (one TMEM round trip)
+                uint32_t v[128];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int kv = kv0 + c + i;
-                            if (kv >= seqlen || (CAUSAL && kv > qpos)) v[i] = 0xFF800000u;   // -inf
+                for (int c = 0; c < 4; ++c)
+                    if (c * 32 < cols) tmem_ld_32x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+                tmem_ld_wait();
+                if (need_mask) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < cols) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int kv = kv0 + c * 32 + i;
+                                if (kv >= seqlen || (CAUSAL && kv > qpos)) v[c * 32 + i] = 0xFF800000u;   // -inf
+                            }
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
                 }
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 < cols) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                            for (int a = 0; a < 4; ++a)
+                                mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(v[c * 32 + i + 2 * a]), __uint_as_float(v[c * 32 + i + 2 * a + 1])));
+                        }
+                    }
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 // ---- lazy rescale of O (warp-uniform decision: tcgen05.ld/st are warp-collective)
                 if (j == 0) {
                     m_used = mx;
@@ -253,68 +309,62 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                     const bool grow = (mx - m_used) * g.scale_log2 > FA_RESCALE_LOG2;
                     if (__any_sync(0xffffffffu, grow)) {
                         const float m_new = fmaxf(m_used, mx);
-                        const float alpha = exp2f((m_used - m_new) * g.scale_log2);
+                        const float alpha = ex2_approx((m_used - m_new) * g.scale_log2);
                         m_used = m_new;
                         l_run *= alpha;
 #pragma unroll 1
                         for (int c = 0; c < HD; c += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(t_o + c, v);
+                            uint32_t o[32];
+                            tmem_ld_32x32(t_o + c, o);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                            tmem_st_32x32(t_o + c, v);
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32(t_o + c, o);
                         }
                     }
                 }
                 const float neg_ms = -m_used * g.scale_log2;
-                // ---- pass 2: P = exp2(S·scale − m·scale) → bf16 pairs → TMEM (over the columns of S already consumed)
-                float rs = 0.f;
-                for (int c = 0; c < cols; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_s + c, v);
-                    tmem_ld_wait();
-                    if (need_mask) {
+                // ---- P = exp2(S·scale − m·scale) → bf16 pairs → TMEM (over the columns of S, already in registers)
+                float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int kv = kv0 + c + i;
-                            if (kv >= seqlen || (CAUSAL && kv > qpos)) v[i] = 0xFF800000u;
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 < cols) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + i]), g.scale_log2, neg_ms));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + i + 1]), g.scale_log2, neg_ms));
+                            rs4[(i >> 1) & 3] += p0 + p1;
+                            pk[i >> 1] = pack_bf16x2(p0, p1);
                         }
+                        tmem_st_32x16(t_s + c * 16, pk);
                     }
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = exp2f(fmaf(__uint_as_float(v[i]), g.scale_log2, neg_ms));
-                        const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), g.scale_log2, neg_ms));
-                        rs += p0 + p1;
-                        pk[i >> 1] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st_32x16(t_s + (c >> 1), pk);
                 }
-                l_run += rs;
+                l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_full[t]);
             }
             // ---- epilogue: O / l → bf16 → global (rows of this sequence only)
-            mbar_wait(&o_full[t], 0);
+            mbar_wait(&o_full[t], n_out & 1);
+            ++n_out;
             tc_fence_after();
-            const bool row_ok = row < nq;
+            const bool row_ok = row < it.nq;
             const float inv = 1.0f / l_run;
-            bf16* dst = g.O + static_cast<long long>(seq_start + qpos) * g.ldo + head * HD;
+            bf16* dst = g.O + static_cast<long long>(it.seq_start + qpos) * g.ldo + it.head * HD;
 #pragma unroll 1
             for (int c = 0; c < HD; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_o + c, v);
+                uint32_t o[32];
+                tmem_ld_32x32(t_o + c, o);
                 tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
                         *reinterpret_cast<uint4*>(dst + c + i) =
-                            make_uint4(pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv),
-                                       pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv),
-                                       pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv),
-                                       pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv));
+                            make_uint4(pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+                                       pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+                                       pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+                                       pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
                     }
                 }
             }
@@ -419,10 +469,10 @@ static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* 
     g.q_offset = q_offset;
     g.chunk = std::min(g.n_sh, 64);          // ≈ 64 × (K+V of one head) stays well inside the 126 MB L2
     g.scale_log2 = scale * 1.4426950408889634f;
-    const int n_chunks = (g.n_sh + g.chunk - 1) / g.chunk;
-    (void)n_chunks;
-    const long long grid = static_cast<long long>(g.n_sh) * g.n_pairs;
-    flash_tc_kernel<HD, CAUSAL><<<static_cast<unsigned>(grid), FA_THREADS, Cfg::SMEM, stream>>>(*tq, *tk, *tv, *tk32, *tv32, g);
+    const long long items = static_cast<long long>(g.n_sh) * g.n_pairs;
+    TEO_CHECK_ARG(items < (1LL << 30), "flash_attention_tc: too many work items");
+    const int grid = static_cast<int>(std::min<long long>(items, h->num_sms));     // persistent: one CTA per SM
+    flash_tc_kernel<HD, CAUSAL><<<grid, FA_THREADS, Cfg::SMEM, stream>>>(*tq, *tk, *tv, *tk32, *tv32, g);
     TEO_LAUNCH_CHECK("flash_tc_kernel");
     h->launches++;
     if (q_offset > 0) {

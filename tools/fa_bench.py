@@ -19,6 +19,8 @@ def main():
     shapes = []
     if which in ("vit", "all"):
         shapes.append(("vit", 64, 16, [257] * 256, False, 1))
+        shapes.append(("vit_q0", 64, 16, [257] * 256, False, 0))       # everything tiled: third tile holds one row
+        shapes.append(("vit256", 64, 16, [256] * 256, False, 0))       # no CLS: two full tiles, two full key blocks
     if which in ("prefill", "all"):
         shapes.append(("prefill", 128, 32, [2130] * 32, True, 0))
     for name, hd, H, lens, causal, qoff in shapes:
