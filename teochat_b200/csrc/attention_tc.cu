@@ -28,13 +28,22 @@ constexpr int FA_THREADS = 384;
 constexpr int FA_TILE_BYTES = 128 * 128;      // [128 rows][64 bf16] under the 128-byte swizzle
 constexpr float FA_RESCALE_LOG2 = 8.0f;       // O is rescaled only when the row max grew by more than 2^8
 
+// Tile configuration per head_dim.  head_dim 128: 128-key blocks, one CTA per SM (TMEM 2·128 + 2·128 = 512 columns,
+// 192 KiB shared memory), the score row of a block held in registers.  head_dim 64 (ViT): 64-key blocks, so that TWO
+// CTAs fit on an SM (TMEM 2·64 + 2·64 = 256 columns each, 80 KiB shared memory, ≤ 80 registers) — four query tiles in
+// flight per SM keep the MUFU (exp2) pipe busy across the softmax → MMA → softmax round trips of each tile.
 template <int HD>
 struct FaCfg {
+    static constexpr int BN = HD == 128 ? 128 : 64;             // keys per block
+    static constexpr int CTAS_PER_SM = HD == 128 ? 1 : 2;
+    static constexpr bool REG_RESIDENT = HD == 128;             // whole score row in registers (one TMEM read)
     static constexpr int HALVES = HD / 64;
-    static constexpr int KV_TILE = HALVES * FA_TILE_BYTES;
-    static constexpr int Q_SET = 2 * KV_TILE;                   // both query tiles of one work item
-    static constexpr int Q_SETS = HD == 128 ? 1 : 2;            // head_dim 64: the next item's Q loads under the current one
-    static constexpr int STAGES = HD == 128 ? 2 : 4;
+    static constexpr int HALF_BYTES = BN * 128;                 // [BN keys][64 bf16] under the 128-byte swizzle
+    static constexpr int KV_TILE = HALVES * HALF_BYTES;
+    static constexpr int Q_SET = 2 * HALVES * FA_TILE_BYTES;    // both query tiles of one work item
+    static constexpr int Q_SETS = 1;
+    static constexpr int STAGES = HD == 128 ? 2 : 3;
+    static constexpr int TMEM_COLS = (2 * BN + 2 * HD <= 256) ? 256 : 512;
     static constexpr int SMEM = Q_SETS * Q_SET + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -56,7 +65,7 @@ struct FaItem {
     int head, seq_start, seqlen, nq, m0, n_tiles, nb[2], nb_max;
     bool valid;
 };
-template <bool CAUSAL>
+template <bool CAUSAL, int BN>
 __device__ __forceinline__ FaItem fa_decode(const FaArgs& g, int idx) {
     FaItem it;
     const int per = g.chunk * g.n_pairs;
@@ -72,13 +81,14 @@ __device__ __forceinline__ FaItem fa_decode(const FaArgs& g, int idx) {
     it.m0 = pair * 256;
     it.valid = it.m0 < it.nq;
     it.n_tiles = (it.nq - it.m0 > 128) ? 2 : 1;
-    const int nb_all = (it.seqlen + 127) >> 7;
-    it.nb[0] = CAUSAL ? min(nb_all, (it.m0 >> 7) + 1) : nb_all;
-    it.nb[1] = it.n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (it.m0 >> 7) + 2) : nb_all);
+    const int nb_all = (it.seqlen + BN - 1) / BN;
+    it.nb[0] = CAUSAL ? min(nb_all, (it.m0 + 127) / BN + 1) : nb_all;          // blocks up to the tile's last row
+    it.nb[1] = it.n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (it.m0 + 255) / BN + 1) : nb_all);
     it.nb_max = max(it.nb[0], it.nb[1]);
     return it;
 }
-__device__ __forceinline__ int fa_block_cols(int seqlen, int j) { return min(128, (seqlen - (j << 7) + 31) & ~31); }
+template <int BN>
+__device__ __forceinline__ int fa_block_cols(int seqlen, int j) { return min(BN, (seqlen - j * BN + 31) & ~31); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -87,12 +97,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, FaCfg<HD>::CTAS_PER_SM)
 flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv,
                 const __grid_constant__ CUtensorMap tk32, const __grid_constant__ CUtensorMap tv32, const FaArgs g) {
     using Cfg = FaCfg<HD>;
-    constexpr int HALVES = Cfg::HALVES, STAGES = Cfg::STAGES, KV_TILE = Cfg::KV_TILE, Q_SETS = Cfg::Q_SETS;
-    constexpr uint32_t TM_S = 0, TM_O = 256;                    // TMEM column bases: S_t at 128·t, O_t at 256 + HD·t
+    constexpr int HALVES = Cfg::HALVES, STAGES = Cfg::STAGES, KV_TILE = Cfg::KV_TILE, Q_SETS = Cfg::Q_SETS, BN = Cfg::BN;
+    constexpr int HALF_BYTES = Cfg::HALF_BYTES;
+    constexpr uint32_t TM_S = 0, TM_O = 2 * BN;                 // TMEM column bases: S_t at BN·t, O_t at 2·BN + HD·t
     const int n_items = g.n_sh * g.n_pairs;
 
     extern __shared__ uint8_t fa_smem_raw[];
@@ -136,7 +147,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -147,28 +158,28 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         if (lane == 0) {
             uint32_t kv_cnt = 0, q_cnt = 0;
             for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-                const FaItem it = fa_decode<CAUSAL>(g, idx);
+                const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
                 if (!it.valid) continue;
                 const int col0 = it.head * HD;
                 const int qs = q_cnt % Q_SETS;
                 mbar_wait(&q_empty[qs], ((q_cnt / Q_SETS) & 1) ^ 1);
-                mbar_arrive_expect_tx(&q_full[qs], it.n_tiles * KV_TILE);
+                mbar_arrive_expect_tx(&q_full[qs], it.n_tiles * HALVES * FA_TILE_BYTES);
                 for (int t = 0; t < it.n_tiles; ++t)
                     for (int h = 0; h < HALVES; ++h)
                         tma_load_2d(sQ + qs * Cfg::Q_SET + (t * HALVES + h) * FA_TILE_BYTES, &tq, &q_full[qs], col0 + 64 * h,
                                     it.seq_start + g.q_offset + it.m0 + 128 * t);
                 ++q_cnt;
                 auto load_block = [&](uint8_t* dst, const CUtensorMap* big, const CUtensorMap* small, uint64_t* bar, int j) {
-                    const int cols = fa_block_cols(it.seqlen, j), row = it.seq_start + (j << 7);
-                    if (cols == 128) {
+                    const int cols = fa_block_cols<BN>(it.seqlen, j), row = it.seq_start + j * BN;
+                    if (cols == BN) {
                         mbar_arrive_expect_tx(bar, KV_TILE);
-                        for (int h = 0; h < HALVES; ++h) tma_load_2d(dst + h * FA_TILE_BYTES, big, bar, col0 + 64 * h, row);
+                        for (int h = 0; h < HALVES; ++h) tma_load_2d(dst + h * HALF_BYTES, big, bar, col0 + 64 * h, row);
                     } else {                                     // tail block: 32-row boxes, only the rows in use
                         const int n32 = cols >> 5;
                         mbar_arrive_expect_tx(bar, HALVES * n32 * 4096);
                         for (int h = 0; h < HALVES; ++h)
                             for (int i = 0; i < n32; ++i)
-                                tma_load_2d(dst + h * FA_TILE_BYTES + i * 4096, small, bar, col0 + 64 * h, row + 32 * i);
+                                tma_load_2d(dst + h * HALF_BYTES + i * 4096, small, bar, col0 + 64 * h, row + 32 * i);
                     }
                 };
                 for (int j = 0; j < it.nb_max; ++j, ++kv_cnt) {
@@ -188,7 +199,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN_MAJOR;
             uint32_t kv_cnt = 0, q_cnt = 0, n_t[2] = {0, 0};
             for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-                const FaItem it = fa_decode<CAUSAL>(g, idx);
+                const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
                 if (!it.valid) continue;
                 const int qs = q_cnt % Q_SETS;
                 const uint8_t* sQi = sQ + qs * Cfg::Q_SET;
@@ -197,22 +208,22 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 #pragma unroll
                     for (int ks = 0; ks < HD / 16; ++ks) {
                         const uint64_t a = umma_desc_k_sw128(smem_u32(sQi + (t * HALVES + ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
-                        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
-                        umma_bf16(tmem_base + TM_S + 128 * t, a, b, idesc, ks > 0 ? 1u : 0u);
+                        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * HALF_BYTES)) + 2 * (ks & 3);
+                        umma_bf16(tmem_base + TM_S + BN * t, a, b, idesc, ks > 0 ? 1u : 0u);
                     }
                 };
                 auto issue_pv = [&](int t, int stage, int cols, bool first) {   // O_t (+)= P_t · V(stage)   [128 × HD]
                     const uint32_t vbase = smem_u32(sV + stage * KV_TILE);
                     for (int ks = 0; ks < cols / 16; ++ks) {
-                        const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, FA_TILE_BYTES, 1024);
-                        umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + 128 * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                        const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, HALF_BYTES, 1024);
+                        umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + BN * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
                     }
                 };
                 mbar_wait(&q_full[qs], (q_cnt / Q_SETS) & 1);
                 mbar_wait(&k_full[kv_cnt % STAGES], (kv_cnt / STAGES) & 1);
                 tc_fence_after();
                 for (int t = 0; t < it.n_tiles; ++t) {
-                    issue_s(t, kv_cnt % STAGES, fa_block_cols(it.seqlen, 0));
+                    issue_s(t, kv_cnt % STAGES, fa_block_cols<BN>(it.seqlen, 0));
                     umma_commit(&s_full[t]);
                 }
                 umma_commit(&k_empty[kv_cnt % STAGES]);
@@ -220,7 +231,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                 for (int j = 0; j < it.nb_max; ++j) {
                     const uint32_t cv = kv_cnt + j, ck = cv + 1;
                     const int sv = cv % STAGES, sk = ck % STAGES;
-                    const int cols = fa_block_cols(it.seqlen, j);
+                    const int cols = fa_block_cols<BN>(it.seqlen, j);
                     bool v_ready = false;
                     for (int t = 0; t < it.n_tiles; ++t) {
                         if (j >= it.nb[t]) continue;
@@ -236,7 +247,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                         if (j + 1 < it.nb[t]) {
                             mbar_wait(&k_full[sk], (ck / STAGES) & 1);
                             tc_fence_after();
-                            issue_s(t, sk, fa_block_cols(it.seqlen, j + 1));
+                            issue_s(t, sk, fa_block_cols<BN>(it.seqlen, j + 1));
                             umma_commit(&s_full[t]);
                         }
                     }
@@ -254,11 +265,11 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         const int t = (warp - 4) >> 2;
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        const uint32_t t_s = lane_base + TM_S + 128 * t;
+        const uint32_t t_s = lane_base + TM_S + BN * t;
         const uint32_t t_o = lane_base + TM_O + HD * t;
         uint32_t n_blk = 0, n_out = 0;                           // phase counters of s_full[t] / o_full[t]
         for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-            const FaItem it = fa_decode<CAUSAL>(g, idx);
+            const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
             if (!it.valid || t >= it.n_tiles) continue;
             const int seqlen = it.seqlen;
             const int row = it.m0 + 128 * t + quad * 32 + lane;  // among the tiled rows of this sequence
@@ -266,38 +277,57 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
             float m_used = -INFINITY, l_run = 0.f;
             const int nbt = it.nb[t];
             for (int j = 0; j < nbt; ++j, ++n_blk) {
-                const int cols = fa_block_cols(seqlen, j);
-                const int kv0 = j << 7;
-                const bool need_mask = (kv0 + cols > seqlen) || (CAUSAL && j == nbt - 1);
+                const int cols = fa_block_cols<BN>(seqlen, j);
+                const int kv0 = j * BN;
+                // keys past the sequence end, or (causal) past the first row of this tile: element-wise mask needed
+                const bool need_mask = (kv0 + cols > seqlen) || (CAUSAL && kv0 + cols - 1 > it.m0 + 128 * t);
                 mbar_wait(&s_full[t], n_blk & 1);
                 tc_fence_after();
-                // ---- the whole score row of this block → registers (one TMEM round trip)
-                uint32_t v[128];
+                constexpr int NV = Cfg::REG_RESIDENT ? BN : 32;
+                uint32_t v[NV];
+                // chunk c (32 score columns) → registers, masked; REG_RESIDENT keeps all chunks live for the second pass
+                auto fetch = [&](int c, uint32_t(&x)[32]) {
+                    tmem_ld_32x32(t_s + c * 32, x);
+                };
+                auto mask = [&](int c, uint32_t(&x)[32]) {
+                    if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c * 32 < cols) tmem_ld_32x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
-                tmem_ld_wait();
-                if (need_mask) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c * 32 < cols) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int kv = kv0 + c * 32 + i;
-                                if (kv >= seqlen || (CAUSAL && kv > qpos)) v[c * 32 + i] = 0xFF800000u;   // -inf
-                            }
+                        for (int i = 0; i < 32; ++i) {
+                            const int kv = kv0 + c * 32 + i;
+                            if (kv >= seqlen || (CAUSAL && kv > qpos)) x[i] = 0xFF800000u;   // -inf
                         }
                     }
-                }
+                };
                 float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                auto rowmax = [&](const uint32_t(&x)[32]) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 < cols) {
+                    for (int i = 0; i < 32; i += 8) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
+                        for (int a = 0; a < 4; ++a)
+                            mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(x[i + 2 * a]), __uint_as_float(x[i + 2 * a + 1])));
+                    }
+                };
+                // ---- pass 1: row max of the block
+                if constexpr (Cfg::REG_RESIDENT) {
 #pragma unroll
-                            for (int a = 0; a < 4; ++a)
-                                mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(v[c * 32 + i + 2 * a]), __uint_as_float(v[c * 32 + i + 2 * a + 1])));
+                    for (int c = 0; c < BN / 32; ++c)
+                        if (c * 32 < cols) fetch(c, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c) {
+                        if (c * 32 < cols) {
+                            mask(c, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+                            rowmax(reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c) {
+                        if (c * 32 < cols) {
+                            fetch(c, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+                            tmem_ld_wait();
+                            mask(c, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+                            rowmax(reinterpret_cast<uint32_t(&)[32]>(v[0]));
                         }
                     }
                 }
@@ -324,20 +354,30 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                     }
                 }
                 const float neg_ms = -m_used * g.scale_log2;
-                // ---- P = exp2(S·scale − m·scale) → bf16 pairs → TMEM (over the columns of S, already in registers)
+                // ---- pass 2: P = exp2(S·scale − m·scale) → bf16 pairs → TMEM, over the columns of S already consumed
                 float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+                auto expstore = [&](int c, const uint32_t(&x)[32]) {
+                    uint32_t pk[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), g.scale_log2, neg_ms));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), g.scale_log2, neg_ms));
+                        rs4[(i >> 1) & 3] += p0 + p1;
+                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st_32x16(t_s + c * 16, pk);
+                };
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
                     if (c * 32 < cols) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + i]), g.scale_log2, neg_ms));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + i + 1]), g.scale_log2, neg_ms));
-                            rs4[(i >> 1) & 3] += p0 + p1;
-                            pk[i >> 1] = pack_bf16x2(p0, p1);
+                        if constexpr (Cfg::REG_RESIDENT) {
+                            expstore(c, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+                        } else {
+                            fetch(c, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+                            tmem_ld_wait();
+                            mask(c, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+                            expstore(c, reinterpret_cast<uint32_t(&)[32]>(v[0]));
                         }
-                        tmem_st_32x16(t_s + c * 16, pk);
                     }
                 }
                 l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
@@ -372,7 +412,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<512>(tmem_base);
+    if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // Rows the tiled kernel skips (q_offset > 0; the ViT CLS row): one warp per (sequence, head, row), online softmax
@@ -452,11 +492,11 @@ static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* 
         TEO_CUDA(cudaFuncSetAttribute(flash_tc_kernel<HD, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
     }
-    const CUtensorMap *tq, *tk, *tv, *tk32, *tv32;
+    CUtensorMap tq, tk, tv, tk32, tv32;
     const uint64_t cols = static_cast<uint64_t>(n_heads) * HD;
     TEO_TRY(get_tmap_bf16(h, q, total_tokens, cols, ldq, 128, &tq));
-    TEO_TRY(get_tmap_bf16(h, k, total_tokens, cols, ldk, 128, &tk));
-    TEO_TRY(get_tmap_bf16(h, v, total_tokens, cols, ldv, 128, &tv));
+    TEO_TRY(get_tmap_bf16(h, k, total_tokens, cols, ldk, Cfg::BN, &tk));
+    TEO_TRY(get_tmap_bf16(h, v, total_tokens, cols, ldv, Cfg::BN, &tv));
     TEO_TRY(get_tmap_bf16(h, k, total_tokens, cols, ldk, 32, &tk32));
     TEO_TRY(get_tmap_bf16(h, v, total_tokens, cols, ldv, 32, &tv32));
     FaArgs g{};
@@ -471,8 +511,8 @@ static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* 
     g.scale_log2 = scale * 1.4426950408889634f;
     const long long items = static_cast<long long>(g.n_sh) * g.n_pairs;
     TEO_CHECK_ARG(items < (1LL << 30), "flash_attention_tc: too many work items");
-    const int grid = static_cast<int>(std::min<long long>(items, h->num_sms));     // persistent: one CTA per SM
-    flash_tc_kernel<HD, CAUSAL><<<grid, FA_THREADS, Cfg::SMEM, stream>>>(*tq, *tk, *tv, *tk32, *tv32, g);
+    const int grid = static_cast<int>(std::min<long long>(items, h->num_sms * Cfg::CTAS_PER_SM));     // persistent CTAs
+    flash_tc_kernel<HD, CAUSAL><<<grid, FA_THREADS, Cfg::SMEM, stream>>>(tq, tk, tv, tk32, tv32, g);
     TEO_LAUNCH_CHECK("flash_tc_kernel");
     h->launches++;
     if (q_offset > 0) {

@@ -114,9 +114,9 @@ struct teo_handle {
 namespace teo {
 
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements) → TMA descriptor with
-// a {64 cols, box_rows} box under SWIZZLE_128B (cached per handle).
+// a {64 cols, box_rows} box under SWIZZLE_128B (cached per handle; *out is a copy, valid whatever the cache does later).
 int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                  const CUtensorMap** out);
+                  CUtensorMap* out);
 
 struct GemmEpilogue {
     const bf16* bias = nullptr;       // [N]

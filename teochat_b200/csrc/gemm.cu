@@ -473,11 +473,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                  const CUtensorMap** out) {
+                  CUtensorMap* out) {
     TmapKey key{ptr, rows, cols, ld, box_rows};
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
-        *out = &it->second;
+        *out = it->second;
         return TEO_OK;
     }
     EncodeTiledFn enc = get_encode_fn();
@@ -501,20 +501,20 @@ int get_tmap_bf16(teo_handle* h, const void* ptr, uint64_t rows, uint64_t cols, 
                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
         return TEO_ERR_CUDA;
     }
-    if (h->tmaps.size() > 4096) h->tmaps.clear();   // bounded cache
-    auto ins = h->tmaps.emplace(key, m);
-    *out = &ins.first->second;
+    if (h->tmaps.size() > 4096) h->tmaps.clear();   // bounded cache (callers hold copies, never references)
+    h->tmaps.emplace(key, m);
+    *out = m;
     return TEO_OK;
 }
 
 // Weights in the blocked layout [N/128][K/64][128][64] (bf16): 4-D map, box = `nblocks` consecutive 128-row tiles
 // of one k block, i.e. nblocks × 16 KiB contiguous in HBM, written to shared memory as (nblocks·128) rows × 128 B
 // under the same 128-byte swizzle as the 2-D path.
-int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, uint32_t nblocks, const CUtensorMap** out) {
+int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, uint32_t nblocks, CUtensorMap* out) {
     TmapKey key{ptr, N, K, 0xB10CB10CULL, nblocks};
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
-        *out = &it->second;
+        *out = it->second;
         return TEO_OK;
     }
     EncodeTiledFn enc = get_encode_fn();
@@ -538,8 +538,8 @@ int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, ui
         return TEO_ERR_CUDA;
     }
     if (h->tmaps.size() > 4096) h->tmaps.clear();
-    auto ins = h->tmaps.emplace(key, m);
-    *out = &ins.first->second;
+    h->tmaps.emplace(key, m);
+    *out = m;
     return TEO_OK;
 }
 
@@ -580,7 +580,7 @@ extern "C" size_t teo_gemm_workspace_bytes(int M, int N, int K) {
 }
 
 template <int BN>
-static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* tb, const CUtensorMap* tc, const CUtensorMap* tr,
+static int launch_cfg(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                       const GemmArgs& g, int units, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
@@ -589,7 +589,7 @@ static int launch_cfg(teo_handle* h, const CUtensorMap* ta, const CUtensorMap* t
         attr_set = true;
     }
     const int grid = std::min(units, h->num_sms);
-    TEO_CUDA(launch_kc(PDL_GEMM, gemm_tn_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, *ta, *tb, *tc, *tr, g));
+    TEO_CUDA(launch_kc(PDL_GEMM, gemm_tn_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tr, g));
     TEO_LAUNCH_CHECK("gemm_tn_kernel");
     h->launches++;
     return TEO_OK;
@@ -618,7 +618,7 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     g.C = workspace;
     g.ldc = N;
     g.split_stride = static_cast<long long>(M) * N;
-    const CUtensorMap *ta, *tb;
+    CUtensorMap ta, tb;
     g.w_blocked = w_blocked ? 1 : 0;
     if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
     else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
@@ -661,7 +661,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     g.C = C;
     g.ldc = ldc;
     g.K = K;
-    const CUtensorMap *ta, *tb, *tc = nullptr, *tr = nullptr;
+    CUtensorMap ta, tb, tc, tr;
     if (p.swap) {
         g.M = N;   // weight rows on the UMMA M dimension
         g.w_is_a = 1;

@@ -1,1 +1,4 @@
-from teochat_b200.eval.eval import load_model  # noqa: F401
+from teochat_b200.eval.eval import eval, load_model, main  # noqa: F401,A004
+
+if __name__ == "__main__":
+    main()
