@@ -108,9 +108,9 @@ int teo_flash_attention(const void* q, int ldq, const void* k, int ldk, const vo
                         int causal, void* stream);
 /* The same contraction on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed K/V ring) — the path
  * teo_vit_encode / teo_llama_prefill take.  Needs the handle (TMA descriptors are cached there) and the total
- * number of token rows behind q/k/v (= cu_seqlens[n_seqs]).  The first q_offset query rows of every sequence are
- * computed by a warp-per-row kernel instead of a 128-row tile (ViT: 1, so that 257 tokens = CLS + two tiles);
- * q_offset must be 0 when causal.  Same numerics contract as teo_flash_attention (P rounded to bf16). */
+ * number of token rows behind q/k/v (= cu_seqlens[n_seqs]).  q_offset ∈ {0,1}: with 1, row 0 of every sequence is
+ * computed by a spare warp of the CTA from the K/V tiles in shared memory instead of a 128-row tile (ViT: 257
+ * tokens = CLS + two tiles); q_offset must be 0 when causal.  Same numerics contract as teo_flash_attention (P rounded to bf16). */
 int teo_flash_attention_tc(teo_handle* h, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                            int ldo, const void* cu_seqlens, int n_seqs, int max_seqlen, int total_tokens, int n_heads,
                            int head_dim, float scale, int causal, int q_offset, void* stream);

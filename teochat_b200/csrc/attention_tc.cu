@@ -3,17 +3,20 @@
 //   ViT blocks      non-causal, 257 tokens per frame, head_dim 64   (HF CLIPAttention: softmax(q·s kᵀ) v)
 //   LLaMA prefill   causal, ragged batch of ~2.1k-token sequences, head_dim 128 (HF LlamaAttention, fp32 softmax)
 //
-// One CTA owns TWO 128-row query tiles of one (sequence, head) and walks the key/value blocks (128 keys) once:
-//   warp 0        TMA producer: Q tiles once, then K and V blocks into two mbarrier rings (128-byte swizzle;
-//                 head_dim 128 = two 64-column halves per tile)
+// Persistent CTAs walk a list of work items; one item = TWO adjacent 128-row query tiles of one (sequence, head),
+// whose key/value blocks (128 keys at head_dim 128, 64 keys at head_dim 64) are streamed once:
+//   warp 0        TMA producer: the item's Q tiles, then its K and V blocks into two mbarrier rings (128-byte swizzle;
+//                 head_dim 128 = two 64-column halves per tile; tail blocks as 32-row boxes)
 //   warp 1        MMA issuer (one thread): S_t = Q_t·Kᵀ (both operands K-major in shared memory) into TMEM,
 //                 O_t += P_t·V with P_t read from TMEM (A operand) and V MN-major straight from its TMA tile
-//   warp 2        TMEM allocator (512 columns: S0 | S1 | O0 | O1; P_t overlays the first half of S_t)
+//   warp 2        TMEM allocator (S0 | S1 | O0 | O1; P_t overlays the first half of S_t)
+//   warp 3        q_offset = 1 only: row 0 of the sequence (the ViT CLS query) on CUDA cores from the same K/V tiles
 //   warps 4-7     softmax of tile 0, one thread per query row (= TMEM lane): row max, lazy rescale of O
 //   warps 8-11    softmax of tile 1        (only when the running max grows by > 2^8), exp2, bf16 P → TMEM
 // The two tiles ping-pong: while one tile's rows are in softmax, the tensor core runs the other tile's
 // P·V and next Q·Kᵀ.  tcgen05.mma retires in issue order, so the commit that publishes S_t(j+1) also
-// guarantees P_t(j)·V(j) is complete — the softmax warps may rescale O_t right after that wait.
+// guarantees P_t(j)·V(j) is complete — the softmax warps may rescale O_t right after that wait, and the
+// epilogue's read of O_t is ordered before the next item's first P·V by the p_full arrival that follows it.
 //
 // Numerics match flash_fwd_kernel (attention.cu): fp32 scores and statistics, P rounded to bf16 before P·V,
 // fp32 accumulation, one rounding of the output.  Algorithmic work 4·S²·d flop (half if causal).
@@ -50,10 +53,13 @@ struct FaCfg {
 struct FaArgs {
     bf16* O;
     long long ldo;
+    const bf16* Q;              // raw query pointer / row stride: the q_offset row is read directly (not through TMA)
+    long long ldq;
     const int* cu_seqlens;
     int n_heads, n_sh;          // n_sh = sequences × heads
     int n_pairs;                // 256-row query groups per sequence; work items = n_pairs × n_sh
-    int q_offset;               // the first q_offset rows of every sequence are not tiled here (ViT: CLS row)
+    int q_offset;               // 0 | 1: row 0 of every sequence is not tiled but computed by warp 3 from the K/V tiles
+                                // in shared memory (ViT: 257 tokens = CLS row + exactly two 128-row query tiles)
     int chunk;                  // (sequence, head) pairs scheduled together, heavy causal groups first
     float scale_log2;
 };
@@ -79,8 +85,8 @@ __device__ __forceinline__ FaItem fa_decode(const FaArgs& g, int idx) {
     it.seqlen = g.cu_seqlens[seq + 1] - it.seq_start;
     it.nq = it.seqlen - g.q_offset;
     it.m0 = pair * 256;
-    it.valid = it.m0 < it.nq;
-    it.n_tiles = (it.nq - it.m0 > 128) ? 2 : 1;
+    it.valid = it.m0 < it.nq || (g.q_offset == 1 && it.m0 == 0 && it.seqlen > 0);   // a 1-token sequence is only its row 0
+    it.n_tiles = (it.nq - it.m0 > 128) ? 2 : (it.nq - it.m0 > 0 ? 1 : 0);
     const int nb_all = (it.seqlen + BN - 1) / BN;
     it.nb[0] = CAUSAL ? min(nb_all, (it.m0 + 127) / BN + 1) : nb_all;          // blocks up to the tile's last row
     it.nb[1] = it.n_tiles < 2 ? 0 : (CAUSAL ? min(nb_all, (it.m0 + 255) / BN + 1) : nb_all);
@@ -136,9 +142,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&k_full[s], 1);
-            mbar_init(&k_empty[s], 1);
+            mbar_init(&k_empty[s], 1 + g.q_offset);           // MMA commit (+ the row-0 warp)
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1);
+            mbar_init(&v_empty[s], 1 + g.q_offset);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
@@ -260,6 +266,122 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
             }
         }
         __syncwarp();
+    } else if (warp == 3 && g.q_offset == 1) {
+        // ------------------------------------------------------------------ row 0 of every sequence (one warp, mma.sync)
+        // A 16-row flash-attention warp whose only live row is the sequence's row 0: walks the same K/V ring as the
+        // MMA warp, 32 keys at a time — q·kᵀ and p·v on mma.sync m16n8k16 with ldmatrix straight from the 128-byte-
+        // swizzled TMA tiles, online softmax in registers.  ~130 instructions per 32 keys, far off the critical path.
+        // Every block of every item is acknowledged on k_empty / v_empty (count 2), also for items whose row 0
+        // belongs to another item (m0 > 0), so that the barrier phases stay in step.
+        constexpr int KS = HD / 16, DT = HD / 8;
+        const int gq = lane >> 2, tq = lane & 3;
+        uint32_t kv_cnt = 0;
+        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+            const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
+            if (!it.valid) continue;
+            const bool mine = it.m0 == 0;
+            uint32_t qf[KS][2];                                   // A fragments of row 0 (rows 1..15 are zero)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) qf[ks][0] = qf[ks][1] = 0u;
+            if (mine && gq == 0) {
+                const bf16* qp = g.Q + static_cast<long long>(it.seq_start) * g.ldq + it.head * HD;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    qf[ks][0] = *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 2 * tq);
+                    qf[ks][1] = *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8 + 2 * tq);
+                }
+            }
+            float o[DT][4];
+#pragma unroll
+            for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+            float m_run = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < it.nb_max; ++j, ++kv_cnt) {
+                const int st = kv_cnt % STAGES;
+                const uint32_t ph = (kv_cnt / STAGES) & 1;
+                const int kv0 = j * BN;
+                const int n_valid = min(BN, it.seqlen - kv0);
+                mbar_wait(&k_full[st], ph);
+                mbar_wait(&v_full[st], ph);
+                if (mine) {
+                    const uint8_t* sKb = sK + st * KV_TILE;
+                    const uint8_t* sVb = sV + st * KV_TILE;
+                    for (int sub = 0; sub * 32 < n_valid; ++sub) {
+                        // ---- S[0, 32 keys] = q · Kᵀ
+                        float sc[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint32_t a[4] = {qf[ks][0], 0u, qf[ks][1], 0u};
+#pragma unroll
+                            for (int nt = 0; nt < 4; nt += 2) {
+                                uint32_t kf[4];
+                                const int r = sub * 32 + nt * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
+                                const int c = 2 * ks + ((lane >> 3) & 1);
+                                ldmatrix_x4(kf, sKb + (c >> 3) * HALF_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+                                mma_bf16_16816(sc[nt], a, kf[0], kf[1]);
+                                mma_bf16_16816(sc[nt + 1], a, kf[2], kf[3]);
+                            }
+                        }
+                        // ---- online softmax of row 0 (lanes 0-3 hold it; the other lanes carry zero rows)
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                if (sub * 32 + nt * 8 + 2 * tq + c >= n_valid) sc[nt][c] = -INFINITY;
+                                mx = fmaxf(mx, sc[nt][c]);
+                            }
+                        }
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                        const float m_new = fmaxf(m_run, mx);           // sub·32 < n_valid ⇒ key sub·32 is live ⇒ finite
+                        const float msub = m_new * g.scale_log2;
+                        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * g.scale_log2 - msub);
+                        m_run = m_new;
+                        float rs = 0.f;
+                        uint32_t pf[2][4];
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const float p0 = ex2_approx(fmaf(sc[nt][0], g.scale_log2, -msub));   // 0 for masked keys
+                            const float p1 = ex2_approx(fmaf(sc[nt][1], g.scale_log2, -msub));
+                            rs += p0 + p1;
+                            pf[nt >> 1][(nt & 1) * 2] = pack_bf16x2(p0, p1);
+                            pf[nt >> 1][(nt & 1) * 2 + 1] = 0u;             // rows 8..15: nothing
+                        }
+                        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+                        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+                        l_run = l_run * alpha + rs;
+#pragma unroll
+                        for (int dt = 0; dt < DT; ++dt) { o[dt][0] *= alpha; o[dt][1] *= alpha; }
+                        // ---- O[0, :] += P · V
+#pragma unroll
+                        for (int ks2 = 0; ks2 < 2; ++ks2) {
+#pragma unroll
+                            for (int dt = 0; dt < DT; dt += 2) {
+                                uint32_t vf[4];
+                                const int r = sub * 32 + ks2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                                const int c = dt + (lane >> 4);
+                                ldmatrix_x4_trans(vf, sVb + (c >> 3) * HALF_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+                                mma_bf16_16816(o[dt], pf[ks2], vf[0], vf[1]);
+                                mma_bf16_16816(o[dt + 1], pf[ks2], vf[2], vf[3]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&k_empty[st]);
+                    mbar_arrive(&v_empty[st]);
+                }
+            }
+            if (mine && gq == 0) {
+                const float inv = 1.0f / l_run;
+                bf16* op = g.O + static_cast<long long>(it.seq_start) * g.ldo + it.head * HD + 2 * tq;
+#pragma unroll
+                for (int dt = 0; dt < DT; ++dt) *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16x2(o[dt][0] * inv, o[dt][1] * inv);
+            }
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ softmax + epilogue (thread = query row)
         const int t = (warp - 4) >> 2;
@@ -415,73 +537,6 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-// Rows the tiled kernel skips (q_offset > 0; the ViT CLS row): one warp per (sequence, head, row), online softmax
-// over all keys in chunks of 32 (lane = key), P rounded to bf16 like the tiled path, lanes own HD/32 output columns.
-template <int HD>
-__global__ void __launch_bounds__(128)
-attn_rows_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk, const bf16* __restrict__ V,
-                 long long ldv, bf16* __restrict__ O, long long ldo, const int* __restrict__ cu_seqlens, int n_heads, int n_rows,
-                 int n_items, float scale_log2) {
-    constexpr int DPL = HD / 32;                                 // output columns per lane
-    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= n_items) return;
-    const int lane = threadIdx.x & 31;
-    const int r = item % n_rows, sh = item / n_rows;
-    const int seq = sh / n_heads, head = sh - seq * n_heads;
-    const int seq_start = cu_seqlens[seq], seqlen = cu_seqlens[seq + 1] - seq_start;
-    if (r >= seqlen) return;
-    const bf16* qp = Q + static_cast<long long>(seq_start + r) * ldq + head * HD;
-    const bf16* kb = K + static_cast<long long>(seq_start) * ldk + head * HD;
-    const bf16* vb = V + static_cast<long long>(seq_start) * ldv + head * HD;
-    uint4 qv[HD / 8];
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) qv[c] = *reinterpret_cast<const uint4*>(qp + c * 8);
-    float m_run = -INFINITY, l_run = 0.f, acc[DPL];
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-    for (int k0 = 0; k0 < seqlen; k0 += 32) {
-        const int key = k0 + lane;
-        float s = -INFINITY;
-        if (key < seqlen) {
-            const bf16* kp = kb + static_cast<long long>(key) * ldk;
-            float a = 0.f;
-#pragma unroll
-            for (int c = 0; c < HD / 8; ++c) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(kp + c * 8);
-                a += bf16_lo(kv.x) * bf16_lo(qv[c].x) + bf16_hi(kv.x) * bf16_hi(qv[c].x) + bf16_lo(kv.y) * bf16_lo(qv[c].y) +
-                     bf16_hi(kv.y) * bf16_hi(qv[c].y) + bf16_lo(kv.z) * bf16_lo(qv[c].z) + bf16_hi(kv.z) * bf16_hi(qv[c].z) +
-                     bf16_lo(kv.w) * bf16_lo(qv[c].w) + bf16_hi(kv.w) * bf16_hi(qv[c].w);
-            }
-            s = a;
-        }
-        const float m_new = fmaxf(m_run, warp_max(s));           // k0 < seqlen ⇒ at least lane 0 is finite
-        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * scale_log2);
-        const float p = exp2f((s - m_new) * scale_log2);        // 0 for masked lanes
-        l_run = l_run * alpha + warp_sum(p);
-        m_run = m_new;
-        const float pb = __bfloat162float(__float2bfloat16_rn(p));
-#pragma unroll
-        for (int i = 0; i < DPL; ++i) acc[i] *= alpha;
-        const int n = min(32, seqlen - k0);
-        for (int kk = 0; kk < n; ++kk) {
-            const float pk = __shfl_sync(0xffffffffu, pb, kk);
-            const bf16* vp = vb + static_cast<long long>(k0 + kk) * ldv + lane * DPL;
-            if (DPL == 2) {
-                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vp);
-                acc[0] += pk * bf16_lo(vv);
-                acc[1] += pk * bf16_hi(vv);
-            } else {
-#pragma unroll
-                for (int i = 0; i < DPL; ++i) acc[i] += pk * __bfloat162float(vp[i]);
-            }
-        }
-    }
-    const float inv = 1.0f / l_run;
-    bf16* op = O + static_cast<long long>(seq_start + r) * ldo + head * HD + lane * DPL;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) op[i] = __float2bfloat16_rn(acc[i] * inv);
-}
-
 template <int HD, bool CAUSAL>
 static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
                              const int* cu, int n_seqs, int max_seqlen, int total_tokens, int n_heads, float scale, int q_offset,
@@ -502,6 +557,8 @@ static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* 
     FaArgs g{};
     g.O = out;
     g.ldo = ldo;
+    g.Q = q;
+    g.ldq = ldq;
     g.cu_seqlens = cu;
     g.n_heads = n_heads;
     g.n_sh = n_seqs * n_heads;
@@ -515,23 +572,18 @@ static int launch_flash_tc_t(teo_handle* h, const bf16* q, int ldq, const bf16* 
     flash_tc_kernel<HD, CAUSAL><<<grid, FA_THREADS, Cfg::SMEM, stream>>>(tq, tk, tv, tk32, tv32, g);
     TEO_LAUNCH_CHECK("flash_tc_kernel");
     h->launches++;
-    if (q_offset > 0) {
-        const int items = g.n_sh * q_offset;
-        attn_rows_kernel<HD><<<(items + 3) / 4, 128, 0, stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, cu, n_heads, q_offset, items, g.scale_log2);
-        TEO_LAUNCH_CHECK("attn_rows_kernel");
-        h->launches++;
-    }
     return TEO_OK;
 }
 
-// q_offset rows at the start of every sequence go through attn_rows_kernel instead of a (mostly empty) 128-row tile:
-// the ViT passes 1, so that its 257 tokens are the CLS row + exactly two query tiles.
+// q_offset = 1: row 0 of every sequence is computed by a spare warp of the same CTA from the K/V tiles in shared memory
+// instead of a (nearly empty) third 128-row tile: the ViT's 257 tokens are the CLS row + exactly two query tiles.
 int launch_flash_attention_tc(teo_handle* h, const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* out, int ldo,
                               const int* cu_seqlens, int n_seqs, int max_seqlen, int total_tokens, int n_heads, int head_dim,
                               float scale, int causal, int q_offset, cudaStream_t stream) {
     TEO_CHECK_ARG(h && q && k && v && out && cu_seqlens, "flash_attention_tc: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && max_seqlen > 0 && n_heads > 0 && total_tokens > 0, "flash_attention_tc: bad sizes");
-    TEO_CHECK_ARG(q_offset >= 0 && q_offset < max_seqlen && !(causal && q_offset), "flash_attention_tc: bad q_offset %d", q_offset);
+    TEO_CHECK_ARG((q_offset == 0 || q_offset == 1) && q_offset < max_seqlen && !(causal && q_offset),
+                  "flash_attention_tc: q_offset must be 0 or 1 (and 0 when causal), got %d", q_offset);
     TEO_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "flash_attention_tc: output rows must be 16-byte aligned");
     if (head_dim == 64 && !causal)
         return launch_flash_tc_t<64, false>(h, q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, n_seqs, max_seqlen, total_tokens, n_heads, scale, q_offset, stream);

@@ -267,6 +267,7 @@ def test_flash_attention(teo, hd, H, lens, causal):
     (128, 2, [127, 128, 129, 255, 256, 257, 385], True, 0),   # tile / block boundaries
     (128, 32, [2151, 2130], True, 0),            # bench prefill shape (two sequences, all heads)
     (128, 2, [200, 31, 1000], False, 0),
+    (128, 2, [200, 31, 1000, 1], False, 1),       # row-0 warp at head_dim 128, incl. a one-token sequence
 ])
 def test_flash_attention_tc(teo, hd, H, lens, causal, q_offset):
     """tcgen05 flash attention (the path teo_vit_encode / teo_llama_prefill take) vs the fp32 restatement."""
