@@ -132,6 +132,13 @@ size_t teo_decode_attention_workspace_bytes(int n_seqs, int n_heads, int head_di
 int teo_decode_attention(const void* q, int ldq, const void* kv_pages, const void* block_table, int max_pages,
                          const void* seq_lens, void* out, int n_seqs, int n_heads, int head_dim, int page_size,
                          int max_seq_len, float scale, void* workspace, size_t workspace_bytes, void* stream);
+/* Same call with the handle: takes the tensor-core kernel (mma.sync over TMA-swizzled page tiles, TMA descriptor of
+ * the pool cached in the handle) for head_dim 128 / page_size 64 — the form teo_llama_decode_step uses; other shapes
+ * run the CUDA-core kernel.  Rows of a page past the sequence length may hold anything (they are never read into
+ * the result). */
+int teo_decode_attention_h(teo_handle* h, const void* q, int ldq, const void* kv_pages, const void* block_table, int max_pages,
+                           const void* seq_lens, void* out, int n_seqs, int n_heads, int head_dim, int page_size,
+                           int max_seq_len, float scale, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- LLaMA pieces ---------------------------------------------------------------------- */
 /* y = x * rsqrt(mean(x^2)+eps) * w  (HF LlamaRMSNorm; fp32 statistics, one bf16 rounding) */

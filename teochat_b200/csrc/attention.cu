@@ -13,7 +13,10 @@
 //     shared-memory ring signalled by mbarriers, and does the dot products on CUDA cores
 //     (MHA: one query row per KV head, nothing for tensor cores to reuse).  Split partials are
 //     merged by decode_combine_kernel.
+#include <stdlib.h>
+
 #include <cmath>
+#include <type_traits>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -230,6 +233,15 @@ int launch_flash_attention(const bf16* q, int ldq, const bf16* k, int ldk, const
 
 // =============================================================================== paged decode
 constexpr int DEC_THREADS = 128;
+// K+V page pairs in the persistent kernel's ring (TEO_DEC_STAGES=2|3|4 overrides, for measurements)
+static int dec_stages() {
+    static const int n = [] {
+        const char* e = getenv("TEO_DEC_STAGES");
+        const int v = e ? atoi(e) : 2;
+        return (v >= 2 && v <= 4) ? v : 2;
+    }();
+    return n;
+}
 
 // grid (splits, heads, seqs).  Workspace (splits > 1): o_part f32 [seq][head][split][HD], ml f32 [seq][head][split][2].
 template <int HD, int PAGE>
@@ -361,6 +373,183 @@ decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __rest
     }
 }
 
+// Persistent form of decode_attn_kernel (the default): gridDim.x CTAs walk the (sequence, head, split) items
+// i = blockIdx.x, blockIdx.x + gridDim.x, …  and treat their pages as ONE stream — thread 0 keeps the 2-deep page
+// ring full across item boundaries (the next item's first pages are in flight while this item's last page is being
+// reduced), and the next item's query is fetched into registers one item ahead.  With one CTA per item every CTA
+// paid launch + barrier init + q load + first-page latency (≈ 2 µs of a ≈ 20 µs life) with its share of the HBM pipe
+// idle; here that is paid once per kernel.  Same arithmetic, same order of operations as decode_attn_kernel.
+template <int HD, int PAGE, int NST>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_attn_persist_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kv_pages, const int* __restrict__ block_table,
+                           int max_pages, const int* __restrict__ seq_lens, int len_bias, bf16* __restrict__ out,
+                           float* __restrict__ o_part, float* __restrict__ ml_part, int n_heads, int n_splits, int n_items,
+                           float scale_log2) {
+    static_assert(HD % 16 == 0 && PAGE % 8 == 0 && PAGE * 2 <= DEC_THREADS * 8 && HD <= DEC_THREADS, "decode tile shape");
+    constexpr int PAGE_BYTES = PAGE * HD * 2;
+    constexpr int TPT = DEC_THREADS / PAGE >= 2 ? 2 : 1;
+    constexpr int KEYS_PER_PASS = DEC_THREADS / TPT;
+    constexpr int CH = HD / 8 / TPT;
+    constexpr int DCH = HD / 8;
+    constexpr int TG = DEC_THREADS / DCH;
+    extern __shared__ uint8_t dec_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dec_smem_raw) + 127) & ~uintptr_t(127));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + NST * PAGE_BYTES;
+    float* sQ = reinterpret_cast<float*>(sV + NST * PAGE_BYTES);
+    float* sS = sQ + HD;
+    float* sO = sS + PAGE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sO + TG * HD);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    pdl_trigger();
+    pdl_wait();                                  // q, the new K/V rows and seq_lens come from the previous kernels
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // item → (sequence, head, split) and its page range; splits fastest, like the one-CTA-per-item grid
+    auto item_range = [&](int item, int& seq, int& head, int& split, int& len, int& p0, int& p1) {
+        split = item % n_splits;
+        const int sh = item / n_splits;
+        head = sh % n_heads;
+        seq = sh / n_heads;
+        len = seq_lens[seq] + len_bias;
+        const int n_pages = (len + PAGE - 1) / PAGE;
+        const int pps = (n_pages + n_splits - 1) / n_splits;
+        p0 = split * pps;
+        p1 = min(n_pages, p0 + pps);
+    };
+    // ---- loader cursor (thread 0): next page to request, possibly items ahead of the compute cursor
+    int l_item = blockIdx.x, l_seq = 0, l_head = 0, l_p = 0, l_p1 = 0;
+    uint32_t l_cnt = 0;
+    auto loader_next = [&]() {
+        while (l_item < n_items && l_p >= l_p1) {
+            l_item += gridDim.x;
+            if (l_item < n_items) {
+                int split, len;
+                item_range(l_item, l_seq, l_head, split, len, l_p, l_p1);
+            }
+        }
+        if (l_item >= n_items) return;
+        const int buf = l_cnt % NST;
+        const int page = block_table[static_cast<long long>(l_seq) * max_pages + l_p];
+        const bf16* kp = kv_pages + ((static_cast<long long>(page) * 2 + 0) * n_heads + l_head) * (PAGE * HD);
+        const bf16* vp = kv_pages + ((static_cast<long long>(page) * 2 + 1) * n_heads + l_head) * (PAGE * HD);
+        mbar_arrive_expect_tx(&bar[buf], 2 * PAGE_BYTES);
+        bulk_load_1d(sK + buf * PAGE_BYTES, kp, PAGE_BYTES, &bar[buf]);
+        bulk_load_1d(sV + buf * PAGE_BYTES, vp, PAGE_BYTES, &bar[buf]);
+        ++l_p;
+        ++l_cnt;
+    };
+    if (tid == 0) {
+        if (l_item < n_items) {
+            int split, len;
+            item_range(l_item, l_seq, l_head, split, len, l_p, l_p1);
+        }
+        for (int s = 0; s < NST; ++s) loader_next();
+    }
+
+    const int dc = tid % DCH, tg = tid / DCH;   // PV phase: 8 dims [dc*8, dc*8+8) of keys ≡ tg (mod TG)
+    uint32_t c_cnt = 0;                          // pages consumed by this CTA so far (ring stage / phase)
+    float q_next = 0.f;                          // this thread's element of the NEXT item's query
+    if (blockIdx.x < n_items && tid < HD) {
+        int seq, head, split, len, p0, p1;
+        item_range(blockIdx.x, seq, head, split, len, p0, p1);
+        q_next = __bfloat162float(q[static_cast<long long>(seq) * ldq + head * HD + tid]);
+    }
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int seq, head, split, len, p0, p1;
+        item_range(item, seq, head, split, len, p0, p1);
+        if (tid < HD) sQ[tid] = q_next;
+        if (item + static_cast<int>(gridDim.x) < n_items && tid < HD) {
+            int s2, h2, sp2, l2, a2, b2;
+            item_range(item + gridDim.x, s2, h2, sp2, l2, a2, b2);
+            q_next = __bfloat162float(q[static_cast<long long>(s2) * ldq + h2 * HD + tid]);
+        }
+        __syncthreads();                         // sQ ready; the previous item's readers of sO / sS are done
+
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int p = p0; p < p1; ++p, ++c_cnt) {
+            const int buf = c_cnt % NST;
+            mbar_wait(&bar[buf], (c_cnt / NST) & 1);
+            const uint8_t* kb = sK + buf * PAGE_BYTES;
+            const uint8_t* vb = sV + buf * PAGE_BYTES;
+            const int valid = min(PAGE, len - p * PAGE);
+            // ---- scores: TPT threads per key, rotated chunk order (bank-conflict-free 16-byte reads)
+            for (int key0 = 0; key0 < PAGE; key0 += KEYS_PER_PASS) {
+                const int key = key0 + tid / TPT, part = tid % TPT;
+                float sacc = 0.f;
+                if (key < PAGE) {
+                    const int rot = key * TPT + part;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int c = part * CH + ((i + rot) % CH);
+                        const uint4 kv = *reinterpret_cast<const uint4*>(kb + key * (HD * 2) + c * 16);
+                        const float4 q0 = *reinterpret_cast<const float4*>(sQ + c * 8);
+                        const float4 q1 = *reinterpret_cast<const float4*>(sQ + c * 8 + 4);
+                        sacc += bf16_lo(kv.x) * q0.x + bf16_hi(kv.x) * q0.y + bf16_lo(kv.y) * q0.z + bf16_hi(kv.y) * q0.w +
+                                bf16_lo(kv.z) * q1.x + bf16_hi(kv.z) * q1.y + bf16_lo(kv.w) * q1.z + bf16_hi(kv.w) * q1.w;
+                    }
+                }
+                if (TPT == 2) sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                if (key < PAGE && part == 0) sS[key] = key < valid ? sacc : -INFINITY;
+            }
+            __syncthreads();
+            // ---- online softmax (every warp recomputes the page max: no extra barrier)
+            float mx = -INFINITY;
+            for (int i = lane; i < PAGE; i += 32) mx = fmaxf(mx, sS[i]);
+            mx = warp_max(mx);
+            const float m_new = fmaxf(m_run, mx);
+            const float msub = m_new * scale_log2;      // valid ≥ 1 ⇒ finite
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * scale_log2 - msub);
+            m_run = m_new;
+            float psum = 0.f;
+            for (int i = lane; i < PAGE; i += 32) psum += exp2f(sS[i] * scale_log2 - msub);
+            psum = warp_sum(psum);
+            l_run = l_run * alpha + psum;
+            // ---- O += P V : thread owns 8 dims of the keys in its group
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= alpha;
+            for (int key = tg; key < valid; key += TG) {
+                float pr = exp2f(sS[key] * scale_log2 - msub);
+                pr = __bfloat162float(__float2bfloat16_rn(pr));    // P is bf16 in the prefill path too
+                const uint4 vv = *reinterpret_cast<const uint4*>(vb + key * (HD * 2) + dc * 16);
+                acc[0] += pr * bf16_lo(vv.x); acc[1] += pr * bf16_hi(vv.x);
+                acc[2] += pr * bf16_lo(vv.y); acc[3] += pr * bf16_hi(vv.y);
+                acc[4] += pr * bf16_lo(vv.z); acc[5] += pr * bf16_hi(vv.z);
+                acc[6] += pr * bf16_lo(vv.w); acc[7] += pr * bf16_hi(vv.w);
+            }
+            __syncthreads();     // everyone is done with sS and ring slot `buf` …
+            if (tid == 0) loader_next();         // … which takes the next page of this CTA's stream (maybe a later item's)
+        }
+        // ---- reduce the TG key groups, write result / partial
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sO[tg * HD + dc * 8 + j] = acc[j];
+        __syncthreads();
+        for (int d = tid; d < HD; d += DEC_THREADS) {
+            float v = 0.f;
+#pragma unroll
+            for (int gI = 0; gI < TG; ++gI) v += sO[gI * HD + d];
+            if (n_splits == 1) {
+                out[(static_cast<long long>(seq) * n_heads + head) * HD + d] = __float2bfloat16_rn(v / l_run);
+            } else {
+                o_part[((static_cast<long long>(seq) * n_heads + head) * n_splits + split) * HD + d] = v;
+            }
+        }
+        if (n_splits > 1 && tid == 0) {
+            float* ml = ml_part + ((static_cast<long long>(seq) * n_heads + head) * n_splits + split) * 2;
+            ml[0] = m_run;      // -inf when this split had no pages
+            ml[1] = l_run;
+        }
+    }
+}
+
 template <int HD>
 __global__ void decode_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part, bf16* __restrict__ out,
                                       int n_heads, int n_splits, float scale_log2) {
@@ -408,7 +597,7 @@ static int decode_splits(int n_seqs, int n_heads, int max_seq_len, int page_size
 template <int HD, int PAGE>
 static int launch_decode_t(const bf16* q, int ldq, const bf16* kv_pages, const int* block_table, int max_pages, const int* seq_lens,
                            int len_bias, bf16* out, int n_seqs, int n_heads, int splits, float scale, float* o_part, float* ml_part,
-                           cudaStream_t stream) {
+                           int resident_ctas, cudaStream_t stream) {
     constexpr int TG = DEC_THREADS / (HD / 8);
     constexpr int SMEM = 4 * PAGE * HD * 2 + (HD + PAGE + TG * HD) * 4 + 16 + 128;
     static bool attr_set = false;
@@ -417,10 +606,36 @@ static int launch_decode_t(const bf16* q, int ldq, const bf16* kv_pages, const i
         attr_set = true;
     }
     const float sl2 = scale * 1.4426950408889634f;
-    dim3 grid(splits, n_heads, n_seqs);
-    TEO_CUDA(launch_kc(PDL_ATTN, decode_attn_kernel<HD, PAGE>, grid, dim3(DEC_THREADS), SMEM, stream, q, static_cast<long long>(ldq), kv_pages, block_table,
-                      max_pages, seq_lens, len_bias, out, o_part, ml_part, n_heads, sl2));
-    TEO_LAUNCH_CHECK("decode_attn_kernel");
+    static const bool persistent = [] {
+        const char* e = getenv("TEO_DEC_ATTN");           // "v1": one CTA per (split, head, sequence) (A/B measurements)
+        return !(e && e[0] == 'v' && e[1] == '1');
+    }();
+    if (persistent) {
+        const int n_items = splits * n_heads * n_seqs;
+        const int grid_p = std::min(n_items, resident_ctas);
+        auto go = [&](auto nst_tag) -> int {
+            constexpr int NST = decltype(nst_tag)::value;
+            constexpr int SMEM_P = 2 * NST * PAGE * HD * 2 + (HD + PAGE + TG * HD) * 4 + 8 * NST + 128;
+            static bool attr2_set = false;
+            if (!attr2_set) {
+                TEO_CUDA(cudaFuncSetAttribute(decode_attn_persist_kernel<HD, PAGE, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+                attr2_set = true;
+            }
+            TEO_CUDA(launch_kc(PDL_ATTN, decode_attn_persist_kernel<HD, PAGE, NST>, dim3(grid_p), dim3(DEC_THREADS), SMEM_P, stream, q,
+                               static_cast<long long>(ldq), kv_pages, block_table, max_pages, seq_lens, len_bias, out, o_part, ml_part,
+                               n_heads, splits, n_items, sl2));
+            return TEO_OK;
+        };
+        const int nst = dec_stages();
+        TEO_TRY(nst == 3 ? go(std::integral_constant<int, 3>{}) : nst == 4 ? go(std::integral_constant<int, 4>{})
+                                                                         : go(std::integral_constant<int, 2>{}));
+        TEO_LAUNCH_CHECK("decode_attn_persist_kernel");
+    } else {
+        dim3 grid(splits, n_heads, n_seqs);
+        TEO_CUDA(launch_kc(PDL_ATTN, decode_attn_kernel<HD, PAGE>, grid, dim3(DEC_THREADS), SMEM, stream, q, static_cast<long long>(ldq), kv_pages,
+                           block_table, max_pages, seq_lens, len_bias, out, o_part, ml_part, n_heads, sl2));
+        TEO_LAUNCH_CHECK("decode_attn_kernel");
+    }
     if (splits > 1) {
         TEO_CUDA(launch_k(decode_combine_kernel<HD>, dim3(n_heads, n_seqs), dim3(HD), 0, stream, static_cast<const float*>(o_part),
                           static_cast<const float*>(ml_part), out, n_heads, splits, sl2));
@@ -429,13 +644,46 @@ static int launch_decode_t(const bf16* q, int ldq, const bf16* kv_pages, const i
     return TEO_OK;
 }
 
+int launch_decode_attention_mma(teo_handle* h, const bf16* q, int ldq, const bf16* kv_pages, const int* block_table, int max_pages,
+                                const int* seq_lens, int len_bias, bf16* out, int n_seqs, int n_heads, int splits, float scale,
+                                float* o_part, float* ml_part, bool* merged, cudaStream_t stream);
+
 int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* kv_pages, const int* block_table, int max_pages,
                             const int* seq_lens, int len_bias, bf16* out, int n_seqs, int n_heads, int head_dim, int page_size,
                             int max_seq_len, float scale, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TEO_CHECK_ARG(q && kv_pages && block_table && seq_lens && out, "decode_attention: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && n_heads > 0 && max_seq_len > 0, "decode_attention: bad sizes");
     const int num_sms = h ? h->num_sms : 148;
-    const int smem_per_cta = 4 * page_size * head_dim * 2 + (head_dim + page_size + (DEC_THREADS / (head_dim / 8)) * head_dim) * 4 + 144;
+    // Tensor-core kernel (decode_attn_mma.cu) whenever a handle is there to cache the pool's TMA descriptor and the
+    // shape is LLaMA's; TEO_DEC_ATTN=cuda|v1 keeps the CUDA-core kernels of this file (A/B measurements).
+    static const bool allow_mma = [] {
+        const char* e = getenv("TEO_DEC_ATTN");
+        return e == nullptr || (e[0] != 'c' && e[0] != 'v');
+    }();
+    if (h && allow_mma && head_dim == 128 && page_size == 64 && (ldq % 2) == 0 && (reinterpret_cast<uintptr_t>(kv_pages) & 15) == 0) {
+        const int splits = decode_splits(n_seqs, n_heads, max_seq_len, page_size, num_sms, 3);
+        float *o_part = nullptr, *ml_part = nullptr;
+        if (splits > 1) {
+            const size_t need = teo_decode_attention_workspace_bytes(n_seqs, n_heads, head_dim, splits);
+            if (workspace == nullptr || workspace_bytes < need) {
+                set_error("decode_attention: %d splits need %zu workspace bytes, got %zu", splits, need, workspace_bytes);
+                return TEO_ERR_WORKSPACE;
+            }
+            o_part = static_cast<float*>(workspace);
+            ml_part = o_part + static_cast<size_t>(n_seqs) * n_heads * splits * head_dim;
+        }
+        bool merged = false;
+        TEO_TRY(launch_decode_attention_mma(h, q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits,
+                                            scale, o_part, ml_part, &merged, stream));
+        if (splits > 1 && !merged) {
+            TEO_CUDA(launch_k(decode_combine_kernel<128>, dim3(n_heads, n_seqs), dim3(128), 0, stream, static_cast<const float*>(o_part),
+                              static_cast<const float*>(ml_part), out, n_heads, splits, scale * 1.4426950408889634f));
+            TEO_LAUNCH_CHECK("decode_combine_kernel");
+        }
+        h->launches += (splits > 1 && !merged) ? 2 : 1;
+        return TEO_OK;
+    }
+    const int smem_per_cta = 2 * dec_stages() * page_size * head_dim * 2 + (head_dim + page_size + (DEC_THREADS / (head_dim / 8)) * head_dim) * 4 + 8 * dec_stages() + 128;
     const int ctas_per_sm = std::max(1, std::min(16, (227 * 1024) / (smem_per_cta + 1024)));
     int splits = decode_splits(n_seqs, n_heads, max_seq_len, page_size, num_sms, ctas_per_sm);
     float *o_part = nullptr, *ml_part = nullptr;
@@ -450,11 +698,11 @@ int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* k
     }
     int rc;
     if (head_dim == 128 && page_size == 64)
-        rc = launch_decode_t<128, 64>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, stream);
+        rc = launch_decode_t<128, 64>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, num_sms * ctas_per_sm, stream);
     else if (head_dim == 128 && page_size == 16)
-        rc = launch_decode_t<128, 16>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, stream);
+        rc = launch_decode_t<128, 16>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, num_sms * ctas_per_sm, stream);
     else if (head_dim == 64 && page_size == 64)
-        rc = launch_decode_t<64, 64>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, stream);
+        rc = launch_decode_t<64, 64>(q, ldq, kv_pages, block_table, max_pages, seq_lens, len_bias, out, n_seqs, n_heads, splits, scale, o_part, ml_part, num_sms * ctas_per_sm, stream);
     else {
         set_error("decode_attention: (head_dim %d, page_size %d) unsupported; built: (128,64) (128,16) (64,64)", head_dim, page_size);
         return TEO_ERR_UNSUPPORTED;
@@ -478,6 +726,16 @@ extern "C" int teo_flash_attention(const void* q, int ldq, const void* k, int ld
 extern "C" size_t teo_decode_attention_workspace_bytes(int n_seqs, int n_heads, int head_dim, int max_splits) {
     if (max_splits < 1) max_splits = 32;
     return static_cast<size_t>(n_seqs) * n_heads * max_splits * (head_dim + 2) * sizeof(float);
+}
+
+extern "C" int teo_decode_attention_h(teo_handle* h, const void* q, int ldq, const void* kv_pages, const void* block_table, int max_pages,
+                                      const void* seq_lens, void* out, int n_seqs, int n_heads, int head_dim, int page_size,
+                                      int max_seq_len, float scale, void* workspace, size_t workspace_bytes, void* stream) {
+    TEO_CHECK_ARG(h != nullptr, "decode_attention_h: null handle");
+    return launch_decode_attention(h, static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(kv_pages),
+                                   static_cast<const int*>(block_table), max_pages, static_cast<const int*>(seq_lens), 0,
+                                   static_cast<bf16*>(out), n_seqs, n_heads, head_dim, page_size, max_seq_len, scale, workspace,
+                                   workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int teo_decode_attention(const void* q, int ldq, const void* kv_pages, const void* block_table, int max_pages,

@@ -74,6 +74,7 @@ _SIGS = {
     "teo_rope_kv_write": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
     "teo_decode_attention_workspace_bytes": (sz, [i, i, i, i]),
     "teo_decode_attention": (i, [vp, i, vp, vp, i, vp, vp, i, i, i, i, i, f, vp, sz, vp]),
+    "teo_decode_attention_h": (i, [vp, vp, i, vp, vp, i, vp, vp, i, i, i, i, i, f, vp, sz, vp]),
     "teo_rmsnorm": (i, [vp, vp, vp, i, i, f, vp]),
     "teo_swiglu": (i, [vp, vp, i, i, vp]),
     "teo_splice_embed": (i, [vp, vp, vp, vp, i, i, vp]),

@@ -308,26 +308,37 @@ def test_flash_attention_tc_matches_mma_path(teo):
     assert (a.float() - b.float()).abs().max().item() <= 2 ** -7 * a.float().abs().max().item()
 
 
+@pytest.mark.parametrize("with_handle", [False, True], ids=["cuda_cores", "handle"])
 @pytest.mark.parametrize("hd,ps,H,lens", [
     (128, 64, 32, [2151, 580, 64, 65, 1, 4000]),      # forces several KV splits
     (128, 64, 4, [300] * 40),                         # many sequences → single split
+    (128, 64, 3, [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 193]),   # page / sub-block boundaries, odd page counts
     (128, 16, 2, [1, 15, 16, 17, 100]),               # tiny-config page size
 ])
-def test_decode_attention(teo, hd, ps, H, lens):
-    lib, _ = teo
+def test_decode_attention(teo, hd, ps, H, lens, with_handle):
+    """Paged decode attention: `teo_decode_attention` (CUDA-core kernel) and `teo_decode_attention_h` (with the handle:
+    the mma.sync / TMA kernel for head_dim 128, page 64 — what the decode step runs).  Cache rows past each sequence's
+    length are poisoned with NaN: they must never reach the result."""
+    lib, h = teo
     B = len(lens)
     max_pages = max((n + ps - 1) // ps for n in lens)
     n_pages = B * max_pages
     bt = torch.randperm(n_pages).view(B, max_pages).to(torch.int32).to(DEV)
     pages = bf(rnd(n_pages, 2, H, ps, hd, seed=21))
+    for b, n in enumerate(lens):                       # poison everything this sequence does not own
+        for j in range(max_pages):
+            lo = max(0, min(ps, n - j * ps))
+            pages[bt[b, j].item(), :, :, lo:, :] = float("nan")
     q = bf(rnd(B, 3 * H * hd, seed=22))                 # q rows inside a fused qkv buffer (ldq = 3*H*hd)
     sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
     out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=DEV)
     wsb = lib.teo_decode_attention_workspace_bytes(B, H, hd, 32)
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     scale = hd ** -0.5
-    L.check(lib.teo_decode_attention(q.data_ptr(), 3 * H * hd, pages.data_ptr(), bt.data_ptr(), max_pages, sl.data_ptr(), out.data_ptr(),
-                                     B, H, hd, ps, max(lens), scale, ws.data_ptr(), ws.numel(), stream()))
+    args = (q.data_ptr(), 3 * H * hd, pages.data_ptr(), bt.data_ptr(), max_pages, sl.data_ptr(), out.data_ptr(),
+            B, H, hd, ps, max(lens), scale, ws.data_ptr(), ws.numel(), stream())
+    L.check(lib.teo_decode_attention_h(h, *args) if with_handle else lib.teo_decode_attention(*args))
+    torch.cuda.synchronize()
     for b, n in enumerate(lens):
         idx = bt[b, : (n + ps - 1) // ps].long()
         K = pages[idx, 0].permute(0, 2, 1, 3).reshape(-1, H, hd)[:n].float()     # [n,H,hd]
