@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "generated_tokens_per_s"
 UNIT = "tokens/s"
+# CPU legs: one sequence, T=1 frame (context 317), 24 new tokens — context : new ≈ 13:1, close to the benchmark
+# config's 2130 : 256 ≈ 8:1, so the prefill / decode mix of the sample resembles the workload's (≈ 25 s here on 8 vCPUs)
+CPU_SAMPLE = (1, 24)
 INSTRUCTION = ("This is a sequence of images captured at times: <video> "
                "What objects or changes can you see across the images?")
 
@@ -80,6 +83,45 @@ def make_prompt_ids(cfg, n_frames):
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
+def host_cpus() -> int:
+    """CPUs this process may really use: the affinity mask, cut to the cgroup CPU quota when there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def pick_cpu_threads() -> int:
+    """Thread count for the CPU leg: the candidate (powers of two up to the usable CPUs, TEO_CPU_THREADS overrides)
+    that runs a prefill-shaped fp32 matmul fastest.  Taking every visible core is not the fastest choice on a
+    many-socket host or under a cgroup quota (round 1: 32 threads on the GPU box ran 12x slower than 8 here)."""
+    import torch
+    if os.environ.get("TEO_CPU_THREADS"):
+        return max(1, int(os.environ["TEO_CPU_THREADS"]))
+    n = host_cpus()
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 128) if c <= n} | {min(n, 128)})
+    a, b = torch.randn(512, 4096), torch.randn(4096, 4096)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if t < best_t * 0.95:                  # prefer fewer threads unless more is clearly faster
+            best, best_t = c, t
+    return best
+
+
 def cpu_reference_leg(n_frames: int, new_tokens: int, steps: int, warmup: int, seed: int = 1234):
     """The oracle port (kind "port": the reference cannot be imported/compiled here) on all
     host cores: fp32, random-init full-size weights, one sequence per step."""
@@ -89,11 +131,7 @@ def cpu_reference_leg(n_frames: int, new_tokens: int, steps: int, warmup: int, s
     from oracle import weights as OW
     from teochat_b200.config import TeoConfig
     cfg = TeoConfig.full()
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    cores = max(1, min(cores, int(os.environ.get("TEO_CPU_THREADS", "32"))))   # fp32 GEMMs stop scaling (and NUMA hurts) past ~32 threads
+    cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     sd = OW.make_state_dict(cfg, seed, dtype=torch.float32)
     ids = make_prompt_ids(cfg, n_frames)
@@ -118,7 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    T, new = 1, 2                           # bounded sample per step (full config would take hours on CPU)
+    T, new = CPU_SAMPLE                     # bounded sample per step (the full config would take hours on CPU)
     cb = cpu_reference_leg(T, new, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["s_per_sample"] * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -220,7 +258,7 @@ def run_gpu(args):
     roof = decode_attention_roofline(model, cfg, B, S0 + new // 2, dev) if not args.tiny else None
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.tiny:
-        cb = cpu_reference_leg(1, 2, 1, 0)
+        cb = cpu_reference_leg(*CPU_SAMPLE, 1, 0)
 
     if rank == 0:
         k = args.steps
@@ -254,11 +292,17 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of decode_attn_mma_kernel from the one `ncu --set full` capture at
+# exactly (bs=32, S=2258): profiles/r01_decode_attn_mma.txt (1.208262 GB + 8.388864 MB; whole 64-token pages)
+NCU_TRAFFIC = {(32, 2258): 1208262000 + 8388864}
+
+
 def decode_attention_roofline(model, cfg, B, S, dev, iters=20):
-    """Dominant kernel of the decode loop: decode_attn_kernel.  Algorithmic bytes per launch =
+    """Dominant kernel of the decode loop: decode_attn_mma_kernel (+ its split merge), launched exactly as
+    teo_llama_decode_step launches it (with the handle).  Algorithmic bytes per launch =
     Σ_seq 2(K,V)·heads·head_dim·2 B·S = 16 384·S per sequence per layer (524 288·S
-    per token over 32 layers); timed alone with CUDA events on the launching stream on a KV pool of
-    the benchmark's size (36+ GiB per layer set ≫ L2, so every launch streams from HBM)."""
+    per token over 32 layers); timed alone with CUDA events on the launching stream, rotating over 8
+    layer-sized KV pools (8 × 1.2 GB ≫ 126 MB L2, so every launch streams from HBM)."""
     import ctypes as C
 
     import torch
@@ -279,8 +323,9 @@ def decode_attention_roofline(model, cfg, B, S, dev, iters=20):
     stream = torch.cuda.current_stream().cuda_stream
 
     def launch(i):
-        L.check(model.lib.teo_decode_attention(q.data_ptr(), 3 * H * hd, pool[i % n_layers_resident].data_ptr(), bt.data_ptr(), pages_per,
-                                               sl.data_ptr(), out.data_ptr(), B, H, hd, ps, S, hd ** -0.5, ws.data_ptr(), ws.numel(), stream))
+        L.check(model.lib.teo_decode_attention_h(model._h, q.data_ptr(), 3 * H * hd, pool[i % n_layers_resident].data_ptr(), bt.data_ptr(),
+                                                 pages_per, sl.data_ptr(), out.data_ptr(), B, H, hd, ps, S, hd ** -0.5, ws.data_ptr(),
+                                                 ws.numel(), stream))
     for i in range(4):
         launch(i)
     torch.cuda.synchronize(dev)
@@ -295,8 +340,10 @@ def decode_attention_roofline(model, cfg, B, S, dev, iters=20):
     pk = peaks()
     ach = alg_bytes / (ms / 1e3) / 1e9
     del pool
-    return {"kernel": "decode_attn_kernel<128,64>", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " (burst copy)",
+    kernel = "decode_attn_mma_kernel" if (hd, ps) == (128, 64) and os.environ.get("TEO_DEC_ATTN") is None else "decode_attn_persist_kernel"
+    return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get((B, S)) if kernel == "decode_attn_mma_kernel" else None,
+            "peak_source": pk["source"] + " (burst copy)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
             "how": f"bs={B}, S={S}, {iters} launches over 8 rotating layer pools, CUDA events"}
 

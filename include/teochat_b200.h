@@ -87,6 +87,15 @@ int teo_patchify_u8_nhwc(const void* frames_u8, void* patches, int n_frames, int
  * eval/inference.py:52-53) */
 int teo_patchify_f32_nchw(const void* pixel_values, void* patches, int n_frames, int image, int patch, int kpad,
                           void* stream);
+/* The processor's transform chain for ONE image of any size (processing_image.py:15-25: ToTensor → Resize(short
+ * side → S, bicubic, antialias) → CenterCrop(S) → Normalize): src u8 [H,W,3] → dst f32 [3,S,S], the reference's
+ * pixel_values.  The caller passes the geometry torchvision derives on the host: nh x nw = size after Resize
+ * (short side S, long side int(S*long/short)), (top,left) = int(round((n - S)/2)) crop origin.  Rows up to 68 k
+ * pixels wide.  Workspace: teo_resize_workspace_bytes(H, W, S). */
+size_t teo_resize_workspace_bytes(int H, int W, int S);
+int teo_resize_crop_normalize_u8(const void* src_u8, int H, int W, int nh, int nw, int top, int left, int S,
+                                 const float* mean3, const float* std3, void* dst_f32, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* [CLS; patches] + position_embedding → pre_layrnorm (modeling_image.py:645-649):
  * patch_out bf16 [n*np, d] → hidden bf16 [n*(np+1), d] */
 int teo_vit_assemble_preln(const void* patch_out, const void* cls, const void* pos, const void* ln_w,

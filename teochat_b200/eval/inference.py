@@ -53,8 +53,11 @@ def run_inference_single(model, processor, tokenizer, inp, image_paths, conv_mod
     ``temperature <= 0`` selects greedy decoding (the parity path)."""
     prompt, image_paths, stop_str = build_prompt(inp, image_paths, conv_mode, timestamps, prompt_strategy,
                                                  chronological_prefix)
-    tensors = [processor.preprocess(i, return_tensors="pt")["pixel_values"][0] for i in image_paths]
-    tensors = [t.to(model.device, dtype=torch.float32) for t in tensors]
+    if hasattr(processor, "preprocess_device") and getattr(model, "device", torch.device("cpu")).type == "cuda":
+        tensors = list(processor.preprocess_device(list(image_paths), model.device))     # same chain, CUDA kernels
+    else:                                                                                # a reference-style processor
+        tensors = [processor.preprocess(i, return_tensors="pt")["pixel_values"][0] for i in image_paths]
+        tensors = [t.to(model.device, dtype=torch.float32) for t in tensors]
     input_ids = tokenizer_image_token(prompt, tokenizer, IMAGE_TOKEN_INDEX, return_tensors="pt").unsqueeze(0).to(model.device)
     stopping_criteria = KeywordsStoppingCriteria([stop_str], tokenizer, input_ids)
     with torch.inference_mode():
@@ -71,12 +74,15 @@ def run_inference_batch(model, processor, tokenizer, inps: Sequence[str], image_
     """Batched greedy form of run_inference_single: one ViT pass over all frames, one ragged
     prefill, one graph-replayed decode loop.  Result i equals run_inference_single on example i."""
     ids_list, frames = [], []
-    raw = hasattr(processor, "to_uint8_nhwc")
+    on_device = hasattr(processor, "preprocess_device") and getattr(model, "device", torch.device("cpu")).type == "cuda"
     for n, (inp, paths) in enumerate(zip(inps, image_paths_list)):
         ts = timestamps_list[n] if timestamps_list is not None else ()
         prompt, paths, _ = build_prompt(inp, paths, conv_mode, ts, prompt_strategy, chronological_prefix)
         ids_list.append(tokenizer_image_token(prompt, tokenizer, IMAGE_TOKEN_INDEX))
-        frames.append(torch.cat([processor.preprocess(p, return_tensors="pt")["pixel_values"] for p in paths]))
+        if on_device:        # raw uint8 over PCIe, ToTensor/Resize/CenterCrop/Normalize in CUDA (teo_resize_crop_normalize_u8)
+            frames.append(processor.preprocess_device(list(paths), model.device))
+        else:
+            frames.append(torch.cat([processor.preprocess(p, return_tensors="pt")["pixel_values"] for p in paths]))
     outs = model.generate_batch(ids_list, pixel_values=frames, max_new_tokens=max_new_tokens,
                                 temperature=temperature or 0.0, seed=seed)
     return [tokenizer.decode(o).replace("</s>", "").strip() for o in outs]

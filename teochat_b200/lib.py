@@ -66,6 +66,8 @@ _SIGS = {
     "teo_weight_to_blocked": (i, [vp, vp, i, i, vp]),
     "teo_patchify_u8_nhwc": (i, [vp, vp, i, i, i, i, vp]),
     "teo_patchify_f32_nchw": (i, [vp, vp, i, i, i, i, vp]),
+    "teo_resize_workspace_bytes": (sz, [i, i, i]),
+    "teo_resize_crop_normalize_u8": (i, [vp, i, i, i, i, i, i, i, C.POINTER(f), C.POINTER(f), vp, vp, sz, vp]),
     "teo_vit_assemble_preln": (i, [vp, vp, vp, vp, vp, vp, i, i, i, f, vp]),
     "teo_layernorm": (i, [vp, vp, vp, vp, i, i, f, vp]),
     "teo_vit_drop_cls": (i, [vp, vp, i, i, i, vp]),

@@ -74,6 +74,32 @@ class TeoImageProcessor:
     def preprocess(self, images, return_tensors="pt"):
         return self.__call__(images=images, return_tensors=return_tensors)
 
+    # -- the same chain on the GPU ----------------------------------------------------------------
+    def preprocess_device(self, images, device) -> torch.Tensor:
+        """``preprocess`` with the arithmetic on the GPU (`teo_resize_crop_normalize_u8`): each image travels as raw
+        uint8 HWC (a quarter of the float bytes, and at its own size) and ToTensor → Resize → CenterCrop → Normalize run
+        in two kernels per image.  Returns f32 [N,3,S,S] on ``device`` — the reference's pixel_values to fp32 rounding."""
+        import ctypes as C
+
+        from . import lib as L
+        if not isinstance(images, list):
+            images = [images]
+        lib, s = L.load(), self.image_size
+        device = torch.device(device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        out = torch.empty(len(images), 3, s, s, dtype=torch.float32, device=device)
+        mean, std = (C.c_float * 3)(*self.image_mean), (C.c_float * 3)(*self.image_std)
+        for n, im in enumerate(images):
+            arr = np.ascontiguousarray(_load_rgb_u8(im))
+            h, w = arr.shape[:2]
+            nh, nw = (s, int(s * w / h)) if h <= w else (int(s * h / w), s)
+            top, left = int(round((nh - s) / 2.0)), int(round((nw - s) / 2.0))
+            src = torch.from_numpy(arr).to(device, non_blocking=True)
+            ws = torch.empty(lib.teo_resize_workspace_bytes(h, w, s), dtype=torch.uint8, device=device)
+            L.check(lib.teo_resize_crop_normalize_u8(src.data_ptr(), h, w, nh, nw, top, left, s, mean, std, out[n].data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), stream), "teo_resize_crop_normalize_u8")
+        return out
+
     # -- raw uint8 fast path --------------------------------------------------------------------
     def to_uint8_nhwc(self, images: Union[List, "np.ndarray"]) -> torch.Tensor:
         """Frames that are already image_size² → u8 [N,H,W,3] (pinned-host friendly)."""

@@ -415,3 +415,54 @@ def test_gemm_blocked_weights(teo, M, N, K):
     assert torch.equal(out, ref)            # same tiles, same accumulation order: bit-identical
     rc = lib.teo_weight_to_blocked(W.data_ptr(), Wb.data_ptr(), N, K + 8, stream())
     assert rc == -1
+
+
+@pytest.mark.parametrize("h,w,s", [
+    (300, 400, 224), (400, 300, 224),       # landscape / portrait: one side resized + cropped
+    (1024, 1024, 224),                      # xBD / S2Looking tile: 4.57x antialiased downscale
+    (100, 150, 224), (64, 64, 224),         # upscale
+    (225, 224, 224), (224, 224, 224), (224, 500, 224),   # short side already 224: crop + normalise only (exact)
+    (513, 333, 224), (897, 641, 224),       # odd widths: rows start at every 16-byte misalignment
+    (240, 20000, 224),                      # 60 kB rows (> 48 KiB of shared memory)
+    (77, 130, 56),                          # tiny-config image size
+])
+def test_resize_crop_normalize(teo, h, w, s):
+    """`teo_resize_crop_normalize_u8` (through TeoImageProcessor.preprocess_device) against the host processor, which is
+    the reference's chain on torch's own bicubic (processing_image.py:15-25), and against the oracle restatement."""
+    from oracle import preprocess as OP
+    from teochat_b200.processor import TeoImageProcessor
+    rng = np.random.default_rng(h * 31 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    proc = TeoImageProcessor(s)
+    want = proc.preprocess(img)["pixel_values"][0]
+    got = proc.preprocess_device(img, DEV)[0].cpu()
+    assert got.shape == want.shape == (3, s, s)
+    err = (got - want).abs().max().item()
+    assert err <= 2e-5, err                                   # fp32 summation order / min(std)
+    if min(h, w) == s:
+        assert torch.equal(got, want)
+    if h * w <= 1024 * 1024:
+        ora = torch.from_numpy(OP.preprocess_u8_hwc(img, s, proc.image_mean, proc.image_std))
+        assert (got - ora).abs().max().item() <= 2e-5
+
+
+def test_resize_feeds_the_tower_and_bad_args(teo):
+    lib, _ = teo
+    from teochat_b200.processor import TeoImageProcessor
+    proc = TeoImageProcessor(224)
+    imgs = [np.random.default_rng(i).integers(0, 256, (200 + 50 * i, 320, 3), dtype=np.uint8) for i in range(3)]
+    a = proc.preprocess_device(imgs, DEV)
+    b = torch.cat([proc.preprocess(im)["pixel_values"] for im in imgs])
+    assert a.shape == (3, 3, 224, 224) and (a.cpu() - b).abs().max().item() <= 2e-5
+    import ctypes as C
+    m = (C.c_float * 3)(0.5, 0.5, 0.5)
+    src = torch.zeros(100, 100, 3, dtype=torch.uint8, device=DEV)
+    dst = torch.empty(3, 224, 224, device=DEV)
+    ws = torch.empty(lib.teo_resize_workspace_bytes(100, 100, 224), dtype=torch.uint8, device=DEV)
+    ok = (src.data_ptr(), 100, 100, 224, 224, 0, 0, 224, m, m, dst.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    assert lib.teo_resize_crop_normalize_u8(*ok) == 0
+    bad_crop = ok[:5] + (1,) + ok[6:]
+    assert lib.teo_resize_crop_normalize_u8(*bad_crop) < 0 and b"crop" in lib.teo_last_error()
+    no_ws = ok[:11] + (None, 0, stream())
+    assert lib.teo_resize_crop_normalize_u8(*no_ws) < 0 and b"workspace" in lib.teo_last_error()
+    torch.cuda.synchronize()
