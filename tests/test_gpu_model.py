@@ -308,3 +308,47 @@ def test_load_model_from_hf_directory(tmp_path, tiny):
     for k, t in ref_model.w.t.items():
         assert torch.equal(t, model.w.t[k]), k
     assert processor.crop_size["height"] == v.image_size
+
+
+def test_cuda_path_vs_reference_code_golden(tmp_path):
+    """The CUDA path against outputs of the REFERENCE's own code (tests/golden/reference_path.*: the reference's
+    run_inference_single → torchvision transform → CLIPVisionTransformer → feature_select → mlp2x_gelu projector →
+    prepare_inputs_labels_for_multimodal, then HF LLaMA greedy; small widths, real 224²/patch-14 geometry).
+    Same inputs (the reference's fp16-rounded pixel values), north-star bar: projector output and logits within 1e-2,
+    greedy ids equal up to a reference near-tie; then the same examples once more from PNG files through the drop-in
+    run_inference_single (GPU preprocessing) — the decoded string equals the reference's."""
+    from PIL import Image
+
+    import refgolden
+    from teochat_b200.eval.inference import run_inference_single
+    from teochat_b200.processor import TeoImageProcessor
+    from teochat_b200.tokenizer import StubTokenizer
+    cfg, meta, arrays = refgolden.load()
+    model = _model(cfg, meta["seed"])
+    st, n_new = meta["stride"], meta["max_new"]
+    for ci, case in enumerate(meta["cases"]):
+        px = torch.from_numpy(arrays[f"pixel_values_f16_{ci}"]).float()
+        ids = arrays[f"input_ids_{ci}"].tolist()
+        proj = model.encode_images(pixel_values=px.to(DEV)).float().cpu()
+        want = torch.from_numpy(arrays[f"projected_{ci}"])
+        e_proj = ((proj.flatten()[::st] - want).abs().max() / want.abs().max()).item()
+        got, gl = model.generate_batch([ids], pixel_values=[px], max_new_tokens=n_new, return_logits=True)
+        wl = torch.from_numpy(arrays[f"logits_{ci}"])
+        n = compare_tokens(got[0], arrays[f"tokens_{ci}"].tolist(), arrays[f"margin_{ci}"], wl.abs().amax(-1).numpy(), f"reference case {ci}")
+        errs = [((gl[0, s].float().cpu() - wl[s]).abs().max() / wl[s].abs().max()).item() for s in range(n)]
+        print(f"reference case {ci}: projector rel err {e_proj:.2e}; logits rel err {['%.2e' % e for e in errs]}; tokens verified {n}/{n_new}")
+        assert e_proj <= LOGIT_RTOL and n >= 1 and all(e <= LOGIT_RTOL for e in errs)
+        # drop-in API on files: raw u8 → teo_resize_crop_normalize_u8 → … → string
+        paths = []
+        imgs = [np.random.RandomState(s).randint(0, 256, (h, w, 3), dtype=np.uint8) for h, w, s in case["images"]]
+        for k, im in enumerate(imgs):
+            p = str(tmp_path / f"c{ci}_{k}.png")
+            Image.fromarray(im).save(p)
+            paths.append(p)
+        out = run_inference_single(model, TeoImageProcessor(224), StubTokenizer(cfg.llama.vocab_size), case["inp"], paths,
+                                   timestamps=case["timestamps"], prompt_strategy=case["prompt_strategy"],
+                                   chronological_prefix=case["chronological_prefix"], temperature=0, max_new_tokens=n_new)
+        if n == n_new:
+            assert out == case["output"], (out, case["output"])
+    del model
+    torch.cuda.empty_cache()
