@@ -30,6 +30,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Another build of the same sources with extra -D flags (compile-time A/B variants), as lib/variants/<name>.so;
+    select it at run time with TEO_LIB_PATH."""
+    vdir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"{name}.so")
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines], "-shared",
+           *[os.path.join(CSRC, s) for s in SOURCES], "-o", out, "-cudart", "static"]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH

@@ -25,6 +25,7 @@
 // Algorithmic work: 2·M·N·K flop; bytes 2·(M·K + N·K + M·N).
 #include <cuda.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -60,6 +61,7 @@ struct GemmArgs {
     int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
     int w_is_a;                 // operand A holds the (constant) weights: may be fetched before griddepcontrol.wait
     int w_blocked;              // weights stored tile-blocked [N/128][K/64][128][64] (4-D tensor map)
+    unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 
 template <int BN>
@@ -70,6 +72,14 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
+    if (g.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g.trace[blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == TEO_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
@@ -145,6 +155,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
     pdl_trigger();                               // let the next kernel's launch + prologue overlap this one
+    if (threadIdx.x == 0) {
+        if (g.trace) g.trace[blockIdx.x * 8 + 4] = 0;
+        trace_stamp(g, 0);                       // CTA entered
+    }
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_m = (g.M + BM - 1) / BM;
@@ -176,6 +190,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) trace_stamp(g, 1);     // barriers, TMEM, descriptors ready
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -209,7 +224,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 pre = cnt;
             }
+            trace_stamp(g, 2);                   // ring filled with weight tiles
             pdl_wait();
+            trace_stamp(g, 3);                   // predecessor grid complete
             int done = 0;
             Scheduler sc;
             sc.init(g, num_m, num_n, total_kb);
@@ -246,6 +263,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = it.kb0; kb < it.kb1; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
+                    if (g.trace && g.trace[blockIdx.x * 8 + 4] == 0) trace_stamp(g, 4);     // first operand pair landed
                     const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
                     const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
 #pragma unroll
@@ -260,6 +278,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
+            trace_stamp(g, 5);                   // last MMA issued
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -429,11 +448,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (++as == 2) { as = 0; aph ^= 1; }
         }
         if (g.tma_epi && lane == 0) tma_store_wait_all<0>();   // all output tiles written before the CTA retires
+        if (warp == 4 && lane == 0) trace_stamp(g, 6);         // epilogue done
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (threadIdx.x == 0) trace_stamp(g, 7);                   // CTA leaving
 }
 
 // out[r,c] = act(Σ_slots partial[slot][r,c] + bias[c]) + residual[r,c] — fixed summation order (deterministic).
@@ -543,6 +564,16 @@ int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, ui
     return TEO_OK;
 }
 
+// development hook (tools/dec_gemm_bench.py): device buffer of 8 u64 per CTA that the next GEMM launches stamp with
+// %globaltimer at their phase boundaries; nullptr (the default) compiles to one predicated-off branch per stamp
+static unsigned long long* g_gemm_trace = nullptr;
+static int g_gemm_trace_cap = 0;         // launches the buffer holds (used as a ring)
+static long long g_gemm_trace_n = 0;     // launches stamped so far
+static unsigned long long* next_trace_slot() {
+    if (!g_gemm_trace || g_gemm_trace_cap <= 0) return nullptr;
+    return g_gemm_trace + (g_gemm_trace_n++ % g_gemm_trace_cap) * (148 * 8);
+}
+
 struct GemmPlan {
     bool swap;
     int bn;
@@ -608,6 +639,7 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
         return TEO_ERR_WORKSPACE;
     }
     GemmArgs g{};
+    g.trace = next_trace_slot();
     g.M = N;
     g.N = M;
     g.K = K;
@@ -653,6 +685,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
                   "gemm: residual not 16-byte aligned");
     const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
     GemmArgs g{};
+    g.trace = next_trace_slot();
     g.act = ep.act;
     g.out_fp32 = ep.out_fp32;
     g.bias = ep.bias;
@@ -665,7 +698,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     if (p.swap) {
         g.M = N;   // weight rows on the UMMA M dimension
         g.w_is_a = 1;
-        g.N = M;
+            g.N = M;
         g.transposed = 1;
         g.w_blocked = w_blocked ? 1 : 0;
         if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
@@ -772,4 +805,14 @@ extern "C" int teo_weight_to_blocked(const void* w_rowmajor, void* w_blocked, in
                                                                                static_cast<uint4*>(w_blocked), N, K);
     TEO_LAUNCH_CHECK("block_weight_kernel");
     return TEO_OK;
+}
+
+// Development hook, not part of include/teochat_b200.h: see g_gemm_trace.  `launches` slots of 148 x 8 u64, used as a ring;
+// returns the number of launches stamped since the previous call.
+extern "C" long long teo_dbg_gemm_trace(void* device_buffer, int launches) {
+    const long long n = g_gemm_trace_n;
+    g_gemm_trace = static_cast<unsigned long long*>(device_buffer);
+    g_gemm_trace_cap = device_buffer ? launches : 0;
+    g_gemm_trace_n = 0;
+    return n;
 }

@@ -2,6 +2,9 @@
 // embeddings + LayerNorm, RMSNorm, SwiGLU, RoPE + KV-page scatter, splice gather, greedy argmax.
 // All are one-pass, 16-byte-vectorised where the layout allows, fp32 math on bf16 storage.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -353,12 +356,14 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
     const int cols = d / RN_CLUSTER;                 // columns owned by this CTA (multiple of 4)
     const long long base = static_cast<long long>(row) * d + static_cast<long long>(rank) * cols;
     float vals[RN_MAXV][4];
+    uint2 wreg[RN_MAXV];                             // norm weights: fetched with the first wave of loads, used after the syncs
     float sq = 0.f;
 #pragma unroll
     for (int v = 0; v < RN_MAXV; ++v) {
         const int c = (v * RN_THREADS + threadIdx.x) * 4;
         if (c < cols) {
             const uint2 r = *reinterpret_cast<const uint2*>(x + base + c);
+            wreg[v] = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
             const float4 acc = sum_partials4(pi, base + c, rank * cols + c);
             // the residual stream is stored in bf16: round before the statistics, like the unfused chain
             vals[v][0] = __bfloat162float(__float2bfloat16_rn(acc.x + bf16_lo(r.x)));
@@ -388,7 +393,7 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
     for (int v = 0; v < RN_MAXV; ++v) {
         const int c = (v * RN_THREADS + threadIdx.x) * 4;
         if (c < cols) {
-            const uint2 wv = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
+            const uint2 wv = wreg[v];
             const float wf[4] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y)};
             *reinterpret_cast<uint2*>(x + base + c) = make_uint2(pack_bf16x2(vals[v][0], vals[v][1]), pack_bf16x2(vals[v][2], vals[v][3]));
             *reinterpret_cast<uint2*>(y + base + c) = make_uint2(pack_bf16x2((vals[v][0] * rstd) * wf[0], (vals[v][1] * rstd) * wf[1]),
@@ -398,6 +403,8 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
 }
 
 // act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i])
+// One group of four outputs per thread, as many CTAs as that takes: capping the grid at two CTAs per SM (so that the next
+// GEMM's CTAs find room beside this kernel's) measured SLOWER, 9.72 → 9.93 ms per decode step.
 __global__ void reduce_swiglu_kernel(PartialInfo pi, bf16* __restrict__ act, int rows, int inter) {
     pdl_trigger();
     pdl_wait();
@@ -466,21 +473,24 @@ __global__ void reduce_rope_kv_write_kernel(PartialInfo pi, bf16* __restrict__ q
         a = __bfloat162float(__float2bfloat16_rn(x0));
         b = __bfloat162float(__float2bfloat16_rn(x1));
     };
+    // All loads of an iteration are issued before its first store (the compiler cannot prove that the stores into qkv /
+    // the KV page do not alias the partials, so interleaving them would serialise five L2 round trips per thread).
     for (int i = lane * 2; i < half; i += 64) {
         const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
-        float a0, a1, b0, b1;
-        r2(rowbase + i, a0, a1, cnt_q);
-        r2(rowbase + i + half, b0, b1, cnt_q);
-        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
-        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
-        r2(rowbase + hidden + i, a0, a1, cnt_k);
-        r2(rowbase + hidden + i + half, b0, b1, cnt_k);
-        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
-        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
-    }
-    for (int i = lane * 4; i < head_dim; i += 128) {
-        const float4 v = sum_partials4(pi, rowbase + 2 * hidden + i, static_cast<int>(rowbase - row0) + 2 * hidden + i);
-        *reinterpret_cast<uint2*>(vdst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        float qa0, qa1, qb0, qb1, ka0, ka1, kb0, kb1;
+        r2(rowbase + i, qa0, qa1, cnt_q);
+        r2(rowbase + i + half, qb0, qb1, cnt_q);
+        r2(rowbase + hidden + i, ka0, ka1, cnt_k);
+        r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int vi = 2 * i;                                   // lane·4: this lane's four v columns of the same pass
+        const bool has_v = vi < head_dim;
+        if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
+        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(qa0 * c0 - qb0 * s0, qa1 * c1 - qb1 * s1);
+        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(qb0 * c0 + qa0 * s0, qb1 * c1 + qa1 * s1);
+        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(ka0 * c0 - kb0 * s0, ka1 * c1 - kb1 * s1);
+        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(kb0 * c0 + ka0 * s0, kb1 * c1 + ka1 * s1);
+        if (has_v) *reinterpret_cast<uint2*>(vdst + vi) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
 

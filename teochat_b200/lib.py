@@ -97,7 +97,9 @@ EXPORTS = tuple(_SIGS)
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; TEO_LIB_PATH selects another build of the same sources (A/B measurements of compile-time
+    variants, scripts/gpu_dec_ab.sh)."""
+    return os.environ.get("TEO_LIB_PATH") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:
