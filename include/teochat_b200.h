@@ -33,6 +33,11 @@ extern "C" {
 #define TEO_ACT_NONE 0
 #define TEO_ACT_QUICK_GELU 1 /* x*sigmoid(1.702x): CLIP default, configuration_image.py:191 */
 #define TEO_ACT_GELU 2       /* erf GELU: nn.GELU(), multimodal_projector/builder.py:44 */
+/* SwiGLU fused into the gate/up projection (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x)): W [N,K] holds the gate and
+ * up rows interleaved in blocks of 32 (rows 64b..64b+31 = gate rows 32b.., rows 64b+32..64b+63 = up rows 32b..), and C
+ * gets N/2 columns: C[m, 32b+j] = bf16(silu(bf16(g)) * bf16(u)).  Tiled schedule only (M > 128), bf16 output,
+ * N % 128 == 0, no bias / residual. */
+#define TEO_ACT_SWIGLU_PAIRS 3
 
 #define TEO_IMAGE_TOKEN_INDEX (-200) /* videollava/constants.py:9 */
 
@@ -223,7 +228,7 @@ typedef struct {
     const void* qkv_w;      /* [3h, h] (q;k;v) */
     const void* o_w;        /* [h, h] */
     const void* post_norm;  /* [h] */
-    const void* gate_up_w;  /* [2*inter, h] (gate rows then up rows) */
+    const void* gate_up_w;  /* [2*inter, h] (gate rows then up rows, or interleaved: teo_llama_model.gate_up_interleaved) */
     const void* down_w;     /* [h, inter] */
     void* kv_pages;         /* this layer's page pool */
 } teo_llama_layer;
@@ -232,6 +237,8 @@ typedef struct {
     int hidden, inter, heads, layers, vocab, page_size, rope_max_pos;
     float eps;
     int w_blocked;                   /* != 0: qkv_w / o_w / gate_up_w / down_w / lm_head in the blocked layout (embed stays row-major) */
+    int gate_up_interleaved;         /* != 0: gate_up_w rows interleaved in blocks of 32 (TEO_ACT_SWIGLU_PAIRS), inter % 32 == 0;
+                                        0: gate rows then up rows */
     const void *rope_cos, *rope_sin; /* f32 [rope_max_pos, head_dim/2] */
     const void* embed;      /* [vocab, h] */
     const void* final_norm; /* [h] */

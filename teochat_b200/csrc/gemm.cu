@@ -300,7 +300,61 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            if (g.tma_epi) {
+            if (g.tma_epi && g.act == TEO_ACT_SWIGLU_PAIRS) {
+                // ---- SwiGLU fused into the gate/up projection: the weight rows come interleaved in blocks of 32
+                // (…| gate 32 | up 32 |…), so accumulator columns [c, c+32) and [c+32, c+64) are the gate and the up
+                // projection of the SAME 32 outputs.  A warp turns two such 64-column chunks into one 64-column
+                // output chunk — bf16(silu(bf16(g)) · bf16(u)), the rounding points of the unfused chain — and
+                // stores it with the usual TMA box; C has N/2 columns.
+                const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+                for (int oc = hsel; oc < BN / 128; oc += 2) {
+                    const int n_out0 = n_blk * (BN / 2) + oc * 64;
+                    if (2 * n_out0 >= g.N) break;              // warp-uniform
+                    if (lane == 0) tma_store_wait_read<0>();   // previous store has drained the staging buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+                        const int col = oc * 128 + hc * 64;
+                        uint32_t vg[32], vu[32];
+                        if (n_blk * BN + col < g.N) {
+                            tmem_ld_32x32(t_acc + col, vg);
+                            tmem_ld_32x32(t_acc + col + 32, vu);
+                            tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) vg[j] = vu[j] = 0u;
+                        }
+                        if (hc == 1 && (oc + 2 >= BN / 128 || 2 * (n_out0 + 128) >= g.N)) {   // last chunk of this warp
+                            tc_fence_before();
+                            mbar_arrive(&tempty_bar[as]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float gg = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vg[c * 8 + j])));
+                                const float uu = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vu[c * 8 + j])));
+                                x[j] = (gg / (1.0f + expf(-gg))) * uu;
+                            }
+                            const int cc = hc * 4 + c;
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((cc ^ (lane & 7)) << 4)) =
+                                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tma_c, stg, n_out0, row0);
+                        tma_store_commit();
+                    }
+                }
+                if (hsel >= BN / 128 || 2 * (n_blk * (BN / 2) + hsel * 64) >= g.N) {   // this warp owned no chunk of the tile
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                }
+            } else if (g.tma_epi) {
                 // ---- staged path: 64-column chunks → swizzled smem → TMA store
                 const int row0 = m_blk * BM + q * 32;
                 const bool has_res = g.residual != nullptr;
@@ -675,7 +729,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     TEO_CHECK_ARG(h != nullptr, "null handle");
     TEO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive size M=%d N=%d K=%d", M, N, K);
     TEO_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
-    TEO_CHECK_ARG(lda >= K && (w_blocked || ldw >= K) && ldc >= N, "gemm: leading dimension too small");
+    TEO_CHECK_ARG(lda >= K && (w_blocked || ldw >= K) && ldc >= (ep.act == TEO_ACT_SWIGLU_PAIRS ? N / 2 : N),
+                  "gemm: leading dimension too small");
     TEO_CHECK_ARG(!w_blocked || (N % 128 == 0 && K % 64 == 0), "gemm: blocked weights need N %% 128 == 0 and K %% 64 == 0");
     TEO_CHECK_ARG(ldc % (ep.out_fp32 ? 4 : 8) == 0, "gemm: ldc (%d) breaks 16-byte row alignment", ldc);
     TEO_CHECK_ARG(ep.residual == nullptr || ep.ldr % 8 == 0, "gemm: ldr (%d) must be a multiple of 8", ep.ldr);
@@ -684,6 +739,14 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     TEO_CHECK_ARG(ep.residual == nullptr || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0,
                   "gemm: residual not 16-byte aligned");
     const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
+    if (ep.act == TEO_ACT_SWIGLU_PAIRS) {
+        TEO_CHECK_ARG(!ep.out_fp32 && !ep.bias && !ep.residual && N % 128 == 0 && N >= 256,
+                      "gemm: the SwiGLU-pairs epilogue needs bf16 output, no bias/residual and N %% 128 == 0 (N=%d)", N);
+        if (p.swap) {
+            set_error("gemm: the SwiGLU-pairs epilogue runs on the tiled schedule only (M=%d <= 128 takes the swap-AB path)", M);
+            return TEO_ERR_UNSUPPORTED;
+        }
+    }
     GemmArgs g{};
     g.trace = next_trace_slot();
     g.act = ep.act;
@@ -727,7 +790,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
         if (!ep.out_fp32) {           // staged TMA-store epilogue: 32-row × 64-column boxes of C (and of the residual)
             g.tma_epi = 1;
-            TEO_TRY(get_tmap_bf16(h, C, M, N, ldc, 32, &tc));
+            TEO_TRY(get_tmap_bf16(h, C, M, ep.act == TEO_ACT_SWIGLU_PAIRS ? N / 2 : N, ldc, 32, &tc));
             tr = tc;
             if (ep.residual) TEO_TRY(get_tmap_bf16(h, ep.residual, M, N, ep.ldr, 32, &tr));
         }
@@ -759,7 +822,7 @@ extern "C" int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* 
                              int N, int K, const void* bias, const void* residual, int ldr, int act, int out_fp32,
                              void* workspace, size_t workspace_bytes, void* stream) {
     TEO_CHECK_ARG(A && W && C, "gemm: null operand");
-    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_GELU, "gemm: unknown activation %d", act);
+    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_SWIGLU_PAIRS, "gemm: unknown activation %d", act);
     GemmEpilogue ep;
     ep.bias = static_cast<const bf16*>(bias);
     ep.residual = static_cast<const bf16*>(residual);
@@ -774,7 +837,7 @@ extern "C" int teo_gemm_bf16_wblocked(teo_handle* h, const void* A, int lda, con
                                       const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
                                       size_t workspace_bytes, void* stream) {
     TEO_CHECK_ARG(A && W_blocked && C, "gemm: null operand");
-    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_GELU, "gemm: unknown activation %d", act);
+    TEO_CHECK_ARG(act >= TEO_ACT_NONE && act <= TEO_ACT_SWIGLU_PAIRS, "gemm: unknown activation %d", act);
     GemmEpilogue ep;
     ep.bias = static_cast<const bf16*>(bias);
     ep.residual = static_cast<const bf16*>(residual);

@@ -217,15 +217,21 @@ __global__ void drop_cls_kernel(const uint4* __restrict__ hidden, uint4* __restr
     }
 }
 
-__global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict__ out, int rows, int inter) {
+// Column of gate value i of a [rows, 2·inter] gate/up row: [gate | up] halves, or interleaved in blocks of 32
+// (| gate 32 | up 32 |, TEO_ACT_SWIGLU_PAIRS layout); the matching up value sits `up_off` columns further.
+__device__ __forceinline__ long long gate_col(long long c, int interleaved) { return interleaved ? (c / 32) * 64 + (c % 32) : c; }
+
+__global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict__ out, int rows, int inter, int interleaved) {
     const int i8 = inter / 8;
+    const int up_off = interleaved ? 32 : inter;
     const size_t total = static_cast<size_t>(rows) * i8;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const size_t r = i / i8, c = (i % i8) * 8;
+        const size_t gc = static_cast<size_t>(gate_col(static_cast<long long>(c), interleaved));
         float g[8], u[8], y[8];
-        load8(gate_up + r * 2 * inter + c, g);
-        load8(gate_up + r * 2 * inter + inter + c, u);
+        load8(gate_up + r * 2 * inter + gc, g);
+        load8(gate_up + r * 2 * inter + gc + up_off, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] = (g[j] / (1.0f + expf(-g[j]))) * u[j];
         store8(out + r * inter + c, y);
@@ -290,6 +296,64 @@ __global__ void rope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restri
     }
     for (int i = lane * 2; i < head_dim; i += 64)
         *reinterpret_cast<uint32_t*>(vdst + i) = *reinterpret_cast<const uint32_t*>(v + i);
+}
+
+// Same operation with 16-byte accesses (head_dim % 16 == 0, the prefill path: 68 k tokens × 32 heads per layer): one thread
+// owns 8 adjacent dims of the low half and the matching 8 of the high half of one (token, head), rotates q and k, and
+// copies 16 dims of v.  All ten loads are issued before the first store.
+__device__ __forceinline__ void rope8(const uint4& lo, const uint4& hi, const float* c, const float* s, uint4& o_lo, uint4& o_hi) {
+    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, h[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a0 = bf16_lo(l[j]), a1 = bf16_hi(l[j]), b0 = bf16_lo(h[j]), b1 = bf16_hi(h[j]);
+        const float c0 = c[2 * j], c1 = c[2 * j + 1], s0 = s[2 * j], s1 = s[2 * j + 1];
+        ol[j] = pack_bf16x2(a0 * c0 - b0 * s0, a1 * c1 - b1 * s1);
+        oh[j] = pack_bf16x2(b0 * c0 + a0 * s0, b1 * c1 + a1 * s1);
+    }
+    o_lo = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    o_hi = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+}
+__global__ void __launch_bounds__(256)
+rope_kv_write_vec_kernel(bf16* __restrict__ qkv, const int* __restrict__ positions, const int* __restrict__ seq_ids,
+                         bf16* __restrict__ kv_pages, const int* __restrict__ block_table, int max_pages, long long items,
+                         int n_heads, int head_dim, int page_size, const float* __restrict__ rope_cos,
+                         const float* __restrict__ rope_sin) {
+    const int half = head_dim / 2, tpi = half / 8;                 // threads per (token, head)
+    const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long item = gt / tpi;
+    if (item >= items) return;
+    const int part = static_cast<int>(gt % tpi);
+    const int tok = static_cast<int>(item / n_heads), head = static_cast<int>(item % n_heads);
+    const int hidden = n_heads * head_dim;
+    const int pos = positions[tok];
+    const int seq = seq_ids ? seq_ids[tok] : tok;
+    const int page = block_table[static_cast<size_t>(seq) * max_pages + pos / page_size];
+    const int slot = pos % page_size;
+    bf16* q = qkv + static_cast<size_t>(tok) * 3 * hidden + head * head_dim + part * 8;
+    bf16* k = q + hidden;
+    const bf16* v = qkv + static_cast<size_t>(tok) * 3 * hidden + 2 * hidden + head * head_dim + part * 16;
+    bf16* kdst = kv_pages + (((static_cast<size_t>(page) * 2 + 0) * n_heads + head) * page_size + slot) * head_dim + part * 8;
+    bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim + part * 16;
+    const float4* cs = reinterpret_cast<const float4*>(rope_cos + static_cast<size_t>(pos) * half + part * 8);
+    const float4* sn = reinterpret_cast<const float4*>(rope_sin + static_cast<size_t>(pos) * half + part * 8);
+    const uint4 q_lo = *reinterpret_cast<const uint4*>(q), q_hi = *reinterpret_cast<const uint4*>(q + half);
+    const uint4 k_lo = *reinterpret_cast<const uint4*>(k), k_hi = *reinterpret_cast<const uint4*>(k + half);
+    const uint4 v0 = *reinterpret_cast<const uint4*>(v), v1 = *reinterpret_cast<const uint4*>(v + 8);
+    const float4 c0 = cs[0], c1 = cs[1], s0 = sn[0], s1 = sn[1];
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint4 o_lo, o_hi;
+    rope8(q_lo, q_hi, c, sv, o_lo, o_hi);
+    *reinterpret_cast<uint4*>(q) = o_lo;
+    *reinterpret_cast<uint4*>(q + half) = o_hi;
+    rope8(k_lo, k_hi, c, sv, o_lo, o_hi);
+    *reinterpret_cast<uint4*>(k) = o_lo;
+    *reinterpret_cast<uint4*>(k + half) = o_hi;
+    *reinterpret_cast<uint4*>(kdst) = o_lo;
+    *reinterpret_cast<uint4*>(kdst + half) = o_hi;
+    *reinterpret_cast<uint4*>(vdst) = v0;
+    *reinterpret_cast<uint4*>(vdst + 8) = v1;
 }
 
 // ------------------------------------------------------------------------------ decode-step fusions
@@ -405,16 +469,18 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
 // act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i])
 // One group of four outputs per thread, as many CTAs as that takes: capping the grid at two CTAs per SM (so that the next
 // GEMM's CTAs find room beside this kernel's) measured SLOWER, 9.72 → 9.93 ms per decode step.
-__global__ void reduce_swiglu_kernel(PartialInfo pi, bf16* __restrict__ act, int rows, int inter) {
+__global__ void reduce_swiglu_kernel(PartialInfo pi, bf16* __restrict__ act, int rows, int inter, int interleaved) {
     pdl_trigger();
     pdl_wait();
     const int i4 = inter / 4;
+    const int up_off = interleaved ? 32 : inter;
     const long long total = static_cast<long long>(rows) * i4;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / i4, c = (i % i4) * 4;
-        const float4 g = sum_partials4(pi, r * 2 * inter + c, static_cast<int>(c));
-        const float4 u = sum_partials4(pi, r * 2 * inter + inter + c, static_cast<int>(inter + c));
+        const long long gc = gate_col(c, interleaved);
+        const float4 g = sum_partials4(pi, r * 2 * inter + gc, static_cast<int>(gc));
+        const float4 u = sum_partials4(pi, r * 2 * inter + gc + up_off, static_cast<int>(gc + up_off));
         const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
         float o[4];
 #pragma unroll
@@ -717,14 +783,20 @@ extern "C" int teo_vit_drop_cls(const void* hidden, void* feats, int n_frames, i
     TEO_LAUNCH_CHECK("drop_cls_kernel");
     return TEO_OK;
 }
-extern "C" int teo_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream) {
+namespace teo {
+int launch_swiglu(const void* gate_up, void* out, int rows, int inter, int interleaved, cudaStream_t stream) {
     TEO_CHECK_ARG(gate_up && out, "swiglu: null pointer");
     TEO_CHECK_ARG(rows > 0 && inter > 0 && inter % 8 == 0, "swiglu: rows=%d inter=%d", rows, inter);
+    TEO_CHECK_ARG(!interleaved || inter % 32 == 0, "swiglu: the interleaved layout needs inter %% 32 == 0 (inter=%d)", inter);
     const size_t total = static_cast<size_t>(rows) * (inter / 8);
-    swiglu_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(gate_up),
-                                                                                     static_cast<bf16*>(out), rows, inter);
+    swiglu_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(gate_up), static_cast<bf16*>(out), rows, inter,
+                                                           interleaved ? 1 : 0);
     TEO_LAUNCH_CHECK("swiglu_kernel");
     return TEO_OK;
+}
+}  // namespace teo
+extern "C" int teo_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream) {
+    return teo::launch_swiglu(gate_up, out, rows, inter, 0, static_cast<cudaStream_t>(stream));
 }
 extern "C" int teo_splice_embed(const void* embed_tokens, const void* image_feats, const void* src, void* out, int tokens, int d,
                                 void* stream) {
@@ -742,6 +814,16 @@ int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, vo
                          cudaStream_t stream) {
     TEO_CHECK_ARG(qkv && positions && kv_pages && block_table && rope_cos && rope_sin, "rope_kv_write: null pointer");
     TEO_CHECK_ARG(tokens > 0 && n_heads > 0 && head_dim > 0 && head_dim % 4 == 0 && page_size > 0, "rope_kv_write: bad sizes");
+    if (head_dim % 16 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv_pages) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(rope_cos) & 15) == 0 && (reinterpret_cast<uintptr_t>(rope_sin) & 15) == 0 && (n_heads * head_dim) % 8 == 0) {
+        const long long items = static_cast<long long>(tokens) * n_heads;
+        const long long nthreads = items * (head_dim / 16);
+        rope_kv_write_vec_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, stream>>>(
+            static_cast<bf16*>(qkv), positions, seq_ids, static_cast<bf16*>(kv_pages), block_table, max_pages, items, n_heads, head_dim,
+            page_size, rope_cos, rope_sin);
+        TEO_LAUNCH_CHECK("rope_kv_write_vec_kernel");
+        return TEO_OK;
+    }
     const long long warps = static_cast<long long>(tokens) * n_heads;
     const int threads = 256;
     const long long blocks = (warps * 32 + threads - 1) / threads;
@@ -759,11 +841,11 @@ int launch_reduce_residual_rmsnorm(const PartialInfo& pi, bf16* x, const bf16* w
     TEO_LAUNCH_CHECK("reduce_residual_rmsnorm_kernel");
     return TEO_OK;
 }
-int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, cudaStream_t stream) {
+int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, int interleaved, cudaStream_t stream) {
     TEO_CHECK_ARG(pi.P && act && rows > 0 && inter > 0, "reduce_swiglu: bad arguments");
-    TEO_CHECK_ARG(inter % 4 == 0, "reduce_swiglu: inter %% 4 != 0");
+    TEO_CHECK_ARG(inter % 4 == 0 && (!interleaved || inter % 32 == 0), "reduce_swiglu: inter %% 4 != 0 (or %% 32 for the interleaved layout)");
     const long long total = static_cast<long long>(rows) * (inter / 4);
-    TEO_CUDA(launch_k(reduce_swiglu_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, pi, act, rows, inter));
+    TEO_CUDA(launch_k(reduce_swiglu_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, stream, pi, act, rows, inter, interleaved ? 1 : 0));
     TEO_LAUNCH_CHECK("reduce_swiglu_kernel");
     return TEO_OK;
 }

@@ -57,7 +57,8 @@ int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* t
 int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
                        int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
 int launch_reduce_residual_rmsnorm(const PartialInfo& pi, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, cudaStream_t stream);
-int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, cudaStream_t stream);
+int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, int interleaved, cudaStream_t stream);
+int launch_swiglu(const void* gate_up, void* out, int rows, int inter, int interleaved, cudaStream_t stream);
 int launch_reduce_rope_kv_write(const PartialInfo& pi, void* qkv, const int* positions, void* kv_pages,
                                 const int* block_table, int max_pages, int n_seqs, int n_heads, int head_dim, int page_size,
                                 const float* rope_cos, const float* rope_sin, cudaStream_t stream);
@@ -94,7 +95,7 @@ using namespace teo;
 
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" const char* teo_last_error(void) { return g_err; }
-extern "C" int teo_abi_version(void) { return 1; }
+extern "C" int teo_abi_version(void) { return 2; }
 
 extern "C" int teo_create(int device_id, teo_handle** out) {
     TEO_CHECK_ARG(out != nullptr, "teo_create: null out");
@@ -299,15 +300,24 @@ static int llama_layer_mlp(teo_handle* h, const teo_llama_model* m, const teo_ll
                            bf16* gate_up, bf16* act, void* gws, size_t gws_bytes, cudaStream_t stream) {
     const int hd = m->hidden, I = m->inter;
     TEO_TRY(teo_rmsnorm(x, L.post_norm, norm_out, rows, hd, m->eps, stream));
-    GemmEpilogue none;
-    TEO_TRY(launch_gemm(h, norm_out, hd, static_cast<const bf16*>(L.gate_up_w), hd, gate_up, 2 * I, rows, 2 * I, hd, none, gws, gws_bytes,
-                        stream, m->w_blocked));
-    TEO_TRY(teo_swiglu(gate_up, act, rows, I, stream));
+    if (m->gate_up_interleaved && rows > 128) {
+        // tiled GEMM: SwiGLU in the epilogue, the [rows, 2I] gate/up activations never reach HBM
+        GemmEpilogue pairs;
+        pairs.act = TEO_ACT_SWIGLU_PAIRS;
+        TEO_TRY(launch_gemm(h, norm_out, hd, static_cast<const bf16*>(L.gate_up_w), hd, act, I, rows, 2 * I, hd, pairs, gws, gws_bytes, stream,
+                            m->w_blocked));
+    } else {
+        GemmEpilogue none;
+        TEO_TRY(launch_gemm(h, norm_out, hd, static_cast<const bf16*>(L.gate_up_w), hd, gate_up, 2 * I, rows, 2 * I, hd, none, gws, gws_bytes,
+                            stream, m->w_blocked));
+        TEO_TRY(launch_swiglu(gate_up, act, rows, I, m->gate_up_interleaved, stream));
+        h->launches++;
+    }
     GemmEpilogue res;
     res.residual = x;
     res.ldr = hd;
     TEO_TRY(launch_gemm(h, act, I, static_cast<const bf16*>(L.down_w), I, x, hd, rows, hd, I, res, gws, gws_bytes, stream, m->w_blocked));
-    h->launches += 2;
+    h->launches += 1;                  // the RMSNorm (GEMMs and the SwiGLU kernel count themselves)
     return TEO_OK;
 }
 
@@ -445,7 +455,7 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
             // gate/up partials → reduce + SwiGLU
             TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
                                          w.gemm_ws_bytes, &pi, stream, m->w_blocked));
-            TEO_TRY(launch_reduce_swiglu(pi, w.act, n_seqs, I, stream));
+            TEO_TRY(launch_reduce_swiglu(pi, w.act, n_seqs, I, m->gate_up_interleaved, stream));
             // down_proj partials → reduce + residual + the NEXT layer's input RMSNorm (or the final norm)
             TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &pi,
                                          stream, m->w_blocked));

@@ -127,6 +127,7 @@ class TeoModel:
                                    layers=l.num_hidden_layers, vocab=l.vocab_size, page_size=cfg.kv_page_size,
                                    rope_max_pos=self.rope_max_pos, eps=l.rms_norm_eps,
                                    w_blocked=int(bool(self.w.blocked.get("llama"))),
+                                   gate_up_interleaved=int(bool(getattr(self.w, "gate_up_interleaved", False))),
                                    rope_cos=self._rope_cos.data_ptr(), rope_sin=self._rope_sin.data_ptr(),
                                    embed=p("llama.embed"), final_norm=p("llama.final_norm"),
                                    lm_head=p("llama.lm_head"), layer=self._llama_layers)

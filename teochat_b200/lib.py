@@ -12,7 +12,7 @@ from . import build as _build
 _LIB = None
 
 OK = 0
-ACT_NONE, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU_PAIRS = 0, 1, 2, 3
 ACT_BY_NAME = {"none": ACT_NONE, "quick_gelu": ACT_QUICK_GELU, "gelu": ACT_GELU}
 
 vp = C.c_void_p
@@ -45,7 +45,8 @@ class LlamaLayer(C.Structure):
 class LlamaModel(C.Structure):
     _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
                 ("vocab", C.c_int), ("page_size", C.c_int), ("rope_max_pos", C.c_int), ("eps", C.c_float),
-                ("w_blocked", C.c_int), ("rope_cos", vp), ("rope_sin", vp), ("embed", vp), ("final_norm", vp), ("lm_head", vp),
+                ("w_blocked", C.c_int), ("gate_up_interleaved", C.c_int), ("rope_cos", vp), ("rope_sin", vp), ("embed", vp),
+                ("final_norm", vp), ("lm_head", vp),
                 ("layer", C.POINTER(LlamaLayer))]
 
 

@@ -90,7 +90,7 @@ class TeoImageProcessor:
         out = torch.empty(len(images), 3, s, s, dtype=torch.float32, device=device)
         mean, std = (C.c_float * 3)(*self.image_mean), (C.c_float * 3)(*self.image_std)
         for n, im in enumerate(images):
-            arr = np.ascontiguousarray(_load_rgb_u8(im))
+            arr = np.array(_load_rgb_u8(im), order="C")            # own, writable copy (PIL hands out read-only views)
             h, w = arr.shape[:2]
             nh, nw = (s, int(s * w / h)) if h <= w else (int(s * h / w), s)
             top, left = int(round((nh - s) / 2.0)), int(round((nw - s) / 2.0))

@@ -7,7 +7,8 @@ HF state-dict names: ``model.image_tower.image_tower.…`` (CLIP
 Fused layouts (all bf16, row-major, K contiguous — the K-major operands of the tcgen05 GEMM):
   ViT layer   qkv_w [3d,d] = q;k;v rows stacked, qkv_b [3d];   patch_w [d, kpad] (im2col order,
               zero padded from 3·14·14 = 588 to kpad = 640 so K is a whole number of 64-wide tiles)
-  LLaMA layer qkv_w [3h,h] = q;k;v;   gate_up_w [2I,h] = gate;up
+  LLaMA layer qkv_w [3h,h] = q;k;v;   gate_up_w [2I,h] = gate;up while loading, then (I % 32 == 0) interleaved in
+  blocks of 32 rows | gate 32 | up 32 | so the GEMM epilogue can apply SwiGLU (TEO_ACT_SWIGLU_PAIRS)
 
 Two sources: ``from_synthetic`` (counter-based pseudo-normal init generated ON THE GPU by
 teo_init_normal_hash_bf16; std per tensor follows the reference's initialisers,
@@ -133,6 +134,7 @@ class TeoWeights:
         t["llama.lm_head"] = torch.empty(l.vocab_size, h, **bf)
         self.t = t
         self.blocked: Dict[str, bool] = {}
+        self.gate_up_interleaved = False
 
     # HF name → destination view (contiguous row slice of a fused buffer), or None for patch_w
     def _dest(self, name: str) -> Optional[torch.Tensor]:
@@ -227,9 +229,25 @@ class TeoWeights:
         llama = [f"llama.{i}.{n}" for i in range(l.num_hidden_layers) for n in ("qkv_w", "o_w", "gate_up_w", "down_w")] + ["llama.lm_head"]
         return {"vit": vit, "proj": proj, "llama": llama}
 
+    def interleave_gate_up(self) -> "TeoWeights":
+        """gate_up_w [gate; up] → rows interleaved in blocks of 32 (| gate 32 | up 32 |…): accumulator columns c..c+31 and
+        c+32..c+63 of the gate/up GEMM then belong to the same 32 outputs (TEO_ACT_SWIGLU_PAIRS).  Runs once, before the
+        blocked re-layout; needs intermediate_size % 32 == 0 (else the layout stays [gate; up] and SwiGLU is a kernel)."""
+        l = self.cfg.llama
+        I = l.intermediate_size
+        if self.gate_up_interleaved or self.blocked.get("llama") or I % 32 != 0:
+            return self
+        for i in range(l.num_hidden_layers):
+            k = f"llama.{i}.gate_up_w"
+            w = self.t[k]
+            self.t[k] = w.view(2, I // 32, 32, w.shape[1]).permute(1, 0, 2, 3).contiguous().view(2 * I, w.shape[1])
+        self.gate_up_interleaved = True
+        return self
+
     def to_blocked(self) -> "TeoWeights":
         """Re-lay every GEMM weight [N,K] as [N/128][K/64][128][64] (16 KiB contiguous operand tiles) when all
         matrices of a model part allow it; sets ``self.blocked[part]``.  Idempotent."""
+        self.interleave_gate_up()
         for part, keys in self._gemm_weight_groups().items():
             if self.blocked.get(part):
                 continue

@@ -74,6 +74,40 @@ def test_gemm_epilogues(teo, M, N, K, act):
     assert rel_err(x, y + res.float()) < 1e-2
 
 
+@pytest.mark.parametrize("M,I,K", [(300, 512, 256), (257 * 3, 11008, 512), (129, 192, 128), (1000, 64 * 5, 320)])
+@pytest.mark.parametrize("blocked", [False, True], ids=["rowmajor", "blocked"])
+def test_gemm_swiglu_pairs_epilogue(teo, M, I, K, blocked):
+    """TEO_ACT_SWIGLU_PAIRS: gate/up rows interleaved in blocks of 32, C = silu(gate)·up with N/2 columns — equal, bit for
+    bit, to the unfused chain (GEMM → bf16 [gate|up] → teo_swiglu) because the epilogue rounds gate and up to bf16 first."""
+    lib, h = teo
+    if blocked and ((2 * I) % 128 or K % 64):
+        pytest.skip("blocked layout needs N % 128 == 0 and K % 64 == 0")
+    A = bf(rnd(M, K, seed=11))
+    Wg, Wu = bf(rnd(I, K, scale=K ** -0.5, seed=12)), bf(rnd(I, K, scale=K ** -0.5, seed=13))
+    W_cat = torch.cat([Wg, Wu]).contiguous()
+    W_int = W_cat.view(2, I // 32, 32, K).permute(1, 0, 2, 3).contiguous().view(2 * I, K)
+    gu = gemm(teo, A, W_cat)                                   # unfused: bf16 [M, 2I]
+    want = torch.empty(M, I, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.teo_swiglu(gu.data_ptr(), want.data_ptr(), M, I, stream()))
+    ref = torch.nn.functional.silu(gu[:, :I].float()) * gu[:, I:].float()
+    assert rel_err(want, ref) < 1e-2
+    out = torch.full((M, I), float("nan"), dtype=torch.bfloat16, device=DEV)
+    Wd = W_int
+    if blocked:
+        Wd = torch.empty_like(W_int)
+        L.check(lib.teo_weight_to_blocked(W_int.data_ptr(), Wd.data_ptr(), 2 * I, K, stream()))
+        L.check(lib.teo_gemm_bf16_wblocked(h, A.data_ptr(), K, Wd.data_ptr(), out.data_ptr(), I, M, 2 * I, K, None, None, 0, L.ACT_SWIGLU_PAIRS, 0,
+                                           None, 0, stream()))
+    else:
+        L.check(lib.teo_gemm_bf16(h, A.data_ptr(), K, Wd.data_ptr(), K, out.data_ptr(), I, M, 2 * I, K, None, None, 0, L.ACT_SWIGLU_PAIRS, 0,
+                                  None, 0, stream()))
+    assert torch.equal(out, want)
+    # small M takes the swap-AB schedule, which has no such epilogue: refused, not silently wrong
+    rc = lib.teo_gemm_bf16(h, A.data_ptr(), K, W_int.data_ptr(), K, out.data_ptr(), I, 32, 2 * I, K, None, None, 0, L.ACT_SWIGLU_PAIRS, 0,
+                           None, 0, stream())
+    assert rc == -4 and b"tiled schedule" in lib.teo_last_error()
+
+
 def test_gemm_strided_operands(teo):
     """q/k/v-style views: leading dimension larger than the logical width."""
     big = bf(rnd(300, 3 * 256, seed=7))
@@ -184,9 +218,11 @@ def _rotate_half(x):
     return torch.cat([-x[..., h:], x[..., :h]], -1)
 
 
-def test_rope_kv_write(teo):
+@pytest.mark.parametrize("H,hd", [(4, 128), (3, 64), (2, 40)], ids=["vec128", "vec64", "scalar40"])
+def test_rope_kv_write(teo, H, hd):
+    """16-byte kernel (head_dim % 16 == 0) and the scalar one (other head dims) against the rotate-half formula."""
     lib, _ = teo
-    H, hd, ps = 4, 128, 16
+    ps = 16
     lens = [5, 37, 16]
     T, B = sum(lens), len(lens)
     max_pages = 4
