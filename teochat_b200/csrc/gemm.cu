@@ -31,61 +31,10 @@
 #include <mutex>
 
 #include "common.h"
+#include "gemm_common.cuh"
 #include "ptx.cuh"
 
 namespace teo {
-
-constexpr int BM = 128;         // UMMA M
-constexpr int BK = 64;          // 64 bf16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int GEMM_THREADS = 384;     // 4 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
-constexpr int STAGING_BYTES = EPI_WARPS * 4096;   // per warp: 32 rows × 64 bf16 (128 B, swizzled)
-constexpr int GROUP_M = 16;     // rasterisation group (tiles along M sharing W tiles in L2)
-
-struct GemmArgs {
-    int M, N, K;                // GEMM-space sizes (swap-AB: M = weight rows, N = batch rows)
-    void* C;
-    long long ldc;
-    const bf16* bias;
-    const bf16* residual;
-    long long ldr;
-    int act;
-    int out_fp32;
-    int transposed;             // store C[n*ldc + m], bias indexed by m (swap-AB)
-    int streamk;                // small-M schedule: every CTA takes an equal contiguous share of the flattened
-                                // (tile, k-block) space; fp32 partials per (tile, slot), no bias/act/residual here
-    int sk_q;                   // k-blocks per CTA in that schedule
-    long long split_stride;     // elements between partial slots
-    int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
-    int w_is_a;                 // operand A holds the (constant) weights: may be fetched before griddepcontrol.wait
-    int w_blocked;              // weights stored tile-blocked [N/128][K/64][128][64] (4-D tensor map)
-    unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
-};
-
-template <int BN>
-struct GemmCfg {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-__device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
-    if (g.trace) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        g.trace[blockIdx.x * 8 + slot] = t;
-    }
-}
-
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == TEO_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
-    if (act == TEO_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-    return x;
-}
 
 // Work items of one CTA.  Normal schedule: whole tiles, strided over the persistent grid, rasterised in groups of
 // GROUP_M tiles along M.  Stream-K schedule (small M, weight streaming): CTA c owns k-blocks [c·Q, (c+1)·Q) of the
@@ -300,125 +249,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            if (g.tma_epi && g.act == TEO_ACT_SWIGLU_PAIRS) {
-                // ---- SwiGLU fused into the gate/up projection: the weight rows come interleaved in blocks of 32
-                // (…| gate 32 | up 32 |…), so accumulator columns [c, c+32) and [c+32, c+64) are the gate and the up
-                // projection of the SAME 32 outputs.  A warp turns two such 64-column chunks into one 64-column
-                // output chunk — bf16(silu(bf16(g)) · bf16(u)), the rounding points of the unfused chain — and
-                // stores it with the usual TMA box; C has N/2 columns.
-                const int row0 = m_blk * BM + q * 32;
-#pragma unroll 1
-                for (int oc = hsel; oc < BN / 128; oc += 2) {
-                    const int n_out0 = n_blk * (BN / 2) + oc * 64;
-                    if (2 * n_out0 >= g.N) break;              // warp-uniform
-                    if (lane == 0) tma_store_wait_read<0>();   // previous store has drained the staging buffer
-                    __syncwarp();
-#pragma unroll
-                    for (int hc = 0; hc < 2; ++hc) {
-                        const int col = oc * 128 + hc * 64;
-                        uint32_t vg[32], vu[32];
-                        if (n_blk * BN + col < g.N) {
-                            tmem_ld_32x32(t_acc + col, vg);
-                            tmem_ld_32x32(t_acc + col + 32, vu);
-                            tmem_ld_wait();
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) vg[j] = vu[j] = 0u;
-                        }
-                        if (hc == 1 && (oc + 2 >= BN / 128 || 2 * (n_out0 + 128) >= g.N)) {   // last chunk of this warp
-                            tc_fence_before();
-                            mbar_arrive(&tempty_bar[as]);
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float x[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float gg = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vg[c * 8 + j])));
-                                const float uu = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vu[c * 8 + j])));
-                                x[j] = (gg / (1.0f + expf(-gg))) * uu;
-                            }
-                            const int cc = hc * 4 + c;
-                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((cc ^ (lane & 7)) << 4)) =
-                                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                        }
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tma_c, stg, n_out0, row0);
-                        tma_store_commit();
-                    }
-                }
-                if (hsel >= BN / 128 || 2 * (n_blk * (BN / 2) + hsel * 64) >= g.N) {   // this warp owned no chunk of the tile
+            if (g.tma_epi) {
+                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, m_blk, n_blk, stg, rbar, rph, lane, q, hsel, [&] {
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[as]);
-                }
-            } else if (g.tma_epi) {
-                // ---- staged path: 64-column chunks → swizzled smem → TMA store
-                const int row0 = m_blk * BM + q * 32;
-                const bool has_res = g.residual != nullptr;
-#pragma unroll 1
-                for (int cj = hsel; cj < BN / 64; cj += 2) {
-                    const int n0 = n_blk * BN + cj * 64;
-                    if (n0 >= g.N) break;                      // warp-uniform
-                    if (lane == 0) {
-                        tma_store_wait_read<0>();              // previous store has drained the staging buffer
-                        if (has_res) {
-                            mbar_arrive_expect_tx(rbar, 4096);
-                            tma_load_2d(stg, &tma_r, rbar, n0, row0);
-                        }
-                    }
-                    __syncwarp();
-                    uint32_t v0[32], v1[32];
-                    tmem_ld_32x32(t_acc + cj * 64, v0);
-                    tmem_ld_32x32(t_acc + cj * 64 + 32, v1);
-                    tmem_ld_wait();
-                    if (cj + 2 >= BN / 64 || n0 + 128 >= g.N) {   // last chunk of this warp: accumulator stage is free
-                        tc_fence_before();
-                        mbar_arrive(&tempty_bar[as]);
-                    }
-                    if (has_res) {
-                        mbar_wait(rbar, rph);
-                        rph ^= 1;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
-                        float x[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
-                        const int n = n0 + c * 8;
-                        if (g.bias && n < g.N) {
-                            const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n);
-                            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
-                        }
-                        if (g.act != TEO_ACT_NONE) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
-                        }
-                        uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
-                        if (has_res) {
-                            const uint4 rv = *slot;
-                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
-                        }
-                        *slot = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                           pack_bf16x2(x[6], x[7]));
-                    }
-                    fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tma_c, stg, n0, row0);
-                        tma_store_commit();
-                    }
-                }
-                if (hsel >= BN / 64 || n_blk * BN + hsel * 64 >= g.N) {   // this warp owned no chunk of the tile
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[as]);
-                }
+                });
             } else {
                 // ---- direct path: fp32 / split-K partial / transposed (swap-AB) outputs
                 const int m = m_blk * BM + q * 32 + lane;
@@ -628,6 +463,10 @@ static unsigned long long* next_trace_slot() {
     return g_gemm_trace + (g_gemm_trace_n++ % g_gemm_trace_cap) * (148 * 8);
 }
 
+bool gemm_pair_enabled();
+int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                     const GemmArgs& g, cudaStream_t stream);
+
 struct GemmPlan {
     bool swap;
     int bn;
@@ -784,6 +623,17 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         g.N = N;
         g.transposed = 0;
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, BM, &ta));
+        if (p.bn == 256 && !ep.out_fp32 && gemm_pair_enabled()) {
+            // large tiled GEMM with bf16 output: the CTA-pair kernel (gemm_pair.cu), 256 x 256 tiles, each CTA loads 128 W rows
+            g.w_blocked = w_blocked ? 1 : 0;
+            g.tma_epi = 1;
+            if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &tb));
+            else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &tb));
+            TEO_TRY(get_tmap_bf16(h, C, M, ep.act == TEO_ACT_SWIGLU_PAIRS ? N / 2 : N, ldc, 32, &tc));
+            tr = tc;
+            if (ep.residual) TEO_TRY(get_tmap_bf16(h, ep.residual, M, N, ep.ldr, 32, &tr));
+            return launch_gemm_pair(h, ta, tb, tc, tr, g, stream);
+        }
         g.w_blocked = (w_blocked && p.bn >= 128) ? 1 : 0;
         TEO_CHECK_ARG(!w_blocked || p.bn >= 128, "gemm: blocked weights need N >= 128");
         if (g.w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, p.bn / 128, &tb));

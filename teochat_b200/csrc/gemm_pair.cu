@@ -1,0 +1,203 @@
+// CTA-pair GEMM (tcgen05 cta_group::2) for the large tiled GEMMs of the hot path — LLaMA prefill (qkv / o / gate_up /
+// down over ~68 k tokens) and the ViT / projector linears: C[M,N] = epi(A[M,K] · W[N,K]^T), bf16 in, fp32 accumulate in
+// TMEM, bf16 out through the staged TMA-store epilogue of gemm_common.cuh.
+//
+// A cluster of two CTAs (the two SMs of a TPC) owns a 256 × 256 output tile.  Per 64-wide k-block each CTA stages its
+// own 128 rows of A and HALF of the W tile (128 of the 256 W rows): 32 KiB per stage instead of the single-CTA kernel's
+// 48 KiB, so the ring is 6 deep and every SM reads a third less shared memory per flop.  The leader CTA (cluster rank 0)
+// issues tcgen05.mma.cta_group::2 (UMMA 256 × 256 × 16); the hardware reads A rows 128..255 and W rows 128..255 from the
+// peer's shared memory at the same offsets and writes each CTA's 128 accumulator rows into that CTA's own TMEM.
+//
+//   warp 0      TMA producer (both CTAs): cp.async.bulk.tensor …cta_group::2, completion bytes credited to the LEADER's
+//               full barrier (which expects both CTAs' 2 × 32 KiB)
+//   warp 1      MMA issuer (leader only): waits full → 4 UMMAs per k-block → tcgen05.commit …multicast frees the ring
+//               slot in BOTH CTAs; after the last k-block a multicast commit publishes the accumulator stage to both
+//   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, the same warp in both CTAs)
+//   warps 4-11  epilogue (both CTAs, each on its own 128 rows): staged_epilogue_tile; the accumulator stage is released
+//               by arriving on the leader's tempty barrier (remote arrive from the peer)
+// Persistent: pair p walks tiles p, p + pairs, … rasterised in groups of 8 tile rows (2048 rows of A stay in L2 while W
+// streams).  Selected by launch_gemm (gemm.cu) for M > 128, N ≥ 256, bf16 output; TEO_GEMM_PAIR=0 keeps the single-CTA
+// kernel (A/B measurements).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.h"
+#include "gemm_common.cuh"
+#include "ptx.cuh"
+
+namespace teo {
+
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_HALF_B_BYTES = (PAIR_BN / 2) * BK * 2;              // 16 KiB: this CTA's half of the W tile
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 KiB
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_TMEM_COLS = 2 * PAIR_BN;                             // two accumulator stages
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+constexpr int PAIR_GROUP_M = 8;                                         // 256-row tile rows per rasterisation group
+
+struct PairTile {
+    int m2, n_blk;
+};
+// tile `unit` of the (num_m2 × num_n) grid, rasterised in groups of PAIR_GROUP_M tile rows, M fastest inside a group
+__device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n) {
+    const int group_sz = PAIR_GROUP_M * num_n;
+    const int grp = unit / group_sz;
+    const int first = grp * PAIR_GROUP_M;
+    const int gm = min(PAIR_GROUP_M, num_m2 - first);
+    const int in_grp = unit - grp * group_sz;
+    return {first + in_grp % gm, in_grp / gm};
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs g) {
+    constexpr int BN = PAIR_BN;
+    constexpr int STAGES = PAIR_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* staging = smem + STAGES * PAIR_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);     // used in the leader only
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;                                          // used in the leader only
+    uint64_t* res_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int num_m2 = (g.M + 2 * BM - 1) / (2 * BM);
+    const int num_n = (g.N + BN - 1) / BN;
+    const int total_kb = (g.K + BK - 1) / BK;
+    const int units = num_m2 * num_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_c);
+        tma_prefetch_desc(&tma_r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * EPI_WARPS * 32);       // the epilogue threads of both CTAs
+        }
+        for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair<PAIR_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                  // the peer's barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            pdl_wait();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int unit = pair; unit < units; unit += n_pairs) {
+                const PairTile t = pair_tile(unit, num_m2, num_n);
+                const int m_blk = t.m2 * 2 + rank;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
+                    tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
+                    if (g.w_blocked) tma_load_4d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank);
+                    else tma_load_2d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2));
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int unit = pair; unit < units; unit += n_pairs) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);             // both CTAs' epilogues have drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);                 // both CTAs' halves of the stage have landed
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
+                    const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + s * PAIR_HALF_B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[s], 3);          // frees the ring slot in both CTAs when the MMAs retire
+                    if (kb == total_kb - 1) umma_commit_pair(&tfull_bar[as], 3);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        pdl_wait();
+        const int ew = warp - 4;
+        const int q = ew & 3;
+        const int hsel = ew >> 2;
+        uint8_t* stg = staging + ew * 4096;
+        uint64_t* rbar = &res_bar[ew];
+        uint32_t rph = 0;
+        int as = 0;
+        uint32_t aph = 0;
+        for (int unit = pair; unit < units; unit += n_pairs) {
+            const PairTile t = pair_tile(unit, num_m2, num_n);
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, t.m2 * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
+                tc_fence_before();
+                mbar_arrive_leader(&tempty_bar[as]);
+            });
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                  // neither CTA leaves while the peer may still read its shared memory or signal it
+    if (warp == 2) tmem_dealloc_pair<PAIR_TMEM_COLS>(tmem_base);
+}
+
+bool gemm_pair_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("TEO_GEMM_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// Called by launch_gemm with the tensor maps already built: ta = A boxes of 128 rows, tb = W boxes of 128 rows (or the
+// 4-D blocked map with one 128-row block per box), tc / tr = 32-row boxes of C and of the residual.
+int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                     const GemmArgs& g, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TEO_CUDA(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int units = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
+    const int pairs = std::max(1, std::min(units, h->num_sms / 2));
+    TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, ta, tb, tc, tr, g));
+    TEO_LAUNCH_CHECK("gemm_pair_kernel");
+    h->launches++;
+    return TEO_OK;
+}
+
+}  // namespace teo

@@ -88,6 +88,62 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
         ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA stages its own 128 rows of A and
+// half of the B tile, the leader (cluster rank 0) issues the MMA, each CTA's TMEM receives its 128 accumulator rows.
+// In a cluster launch the 32-bit shared-window address carries the CTA's rank within the pair in bit 24; clearing it
+// names the same offset in the leader's shared memory (cute::Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// loads whose completion bytes are credited to the LEADER's mbarrier at the same offset as `bar`
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrive on the leader's barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {   // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {        // the same warp of BOTH CTAs
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A · B with M = 256; issued by one thread of the leader CTA only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// when all previously issued pair MMAs retire: one arrival on the barrier at `bar`'s offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
 // 2-D tiled store shared→global (bulk async group; out-of-bounds part of the box is clipped).
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
