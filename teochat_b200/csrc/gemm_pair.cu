@@ -15,7 +15,7 @@
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, the same warp in both CTAs)
 //   warps 4-11  epilogue (both CTAs, each on its own 128 rows): staged_epilogue_tile; the accumulator stage is released
 //               by arriving on the leader's tempty barrier (remote arrive from the peer)
-// Persistent: pair p walks tiles p, p + pairs, … rasterised in groups of 8 tile rows (2048 rows of A stay in L2 while W
+// Persistent: pair p walks tiles p, p + pairs, … rasterised in groups of 16 tile rows (4096 rows of A stay in L2 while W
 // streams).  Selected by launch_gemm (gemm.cu) for M > 128, N ≥ 256, bf16 output; TEO_GEMM_PAIR=0 keeps the single-CTA
 // kernel (A/B measurements).
 #include <stdlib.h>
@@ -34,17 +34,17 @@ constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 KiB
 constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_TMEM_COLS = 2 * PAIR_BN;                             // two accumulator stages
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 1024 + 256;
-constexpr int PAIR_GROUP_M = 8;                                         // 256-row tile rows per rasterisation group
+constexpr int PAIR_GROUP_M = 16;                                        // 256-row tile rows per rasterisation group (4096 rows of A)
 
 struct PairTile {
     int m2, n_blk;
 };
-// tile `unit` of the (num_m2 × num_n) grid, rasterised in groups of PAIR_GROUP_M tile rows, M fastest inside a group
-__device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n) {
-    const int group_sz = PAIR_GROUP_M * num_n;
+// tile `unit` of the (num_m2 × num_n) grid, rasterised in groups of `group_m` tile rows, M fastest inside a group
+__device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n, int group_m) {
+    const int group_sz = group_m * num_n;
     const int grp = unit / group_sz;
-    const int first = grp * PAIR_GROUP_M;
-    const int gm = min(PAIR_GROUP_M, num_m2 - first);
+    const int first = grp * group_m;
+    const int gm = min(group_m, num_m2 - first);
     const int in_grp = unit - grp * group_sz;
     return {first + in_grp % gm, in_grp / gm};
 }
@@ -107,7 +107,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             int s = 0;
             uint32_t ph = 0;
             for (int unit = pair; unit < units; unit += n_pairs) {
-                const PairTile t = pair_tile(unit, num_m2, num_n);
+                const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q);
                 const int m_blk = t.m2 * 2 + rank;
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -157,7 +157,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         int as = 0;
         uint32_t aph = 0;
         for (int unit = pair; unit < units; unit += n_pairs) {
-            const PairTile t = pair_tile(unit, num_m2, num_n);
+            const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q);
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -194,7 +194,17 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
     }
     const int units = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
     const int pairs = std::max(1, std::min(units, h->num_sms / 2));
-    TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, ta, tb, tc, tr, g));
+    // Rasterisation group: W is re-read from HBM once per group of tile rows, so bigger groups mean less DRAM traffic (and
+    // power — the prefill GEMMs run power-capped) until the A panels of a group no longer stay in L2 beside the W stream.
+    // Measured in the full step on one box: 8 rows 869 ms of prefill, 12 849, 16 841, 20 / 24 / 32 slower again; a K-dependent
+    // rule (≈ 32 MiB of A panels) was no better than the constant.  TEO_PAIR_GROUP_M=n overrides (A/B measurements).
+    static const int group_m = [] {
+        const char* e = getenv("TEO_PAIR_GROUP_M");
+        return e ? std::max(1, atoi(e)) : PAIR_GROUP_M;
+    }();
+    GemmArgs ga = g;
+    ga.sk_q = group_m;                                   // (stream-K field, unused by this kernel: carries the group size)
+    TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, ta, tb, tc, tr, ga));
     TEO_LAUNCH_CHECK("gemm_pair_kernel");
     h->launches++;
     return TEO_OK;
