@@ -153,6 +153,7 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tkv, const DmArgs g) 
 #pragma unroll
         for (int i = 0; i < DT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
+        const bool w0_first = (n & 1) == 0;                        // which consumer gets the item's first, third, … page
         for (int p = p0; p < p1; ++p, ++n) {
             if ((n & 1) != static_cast<uint32_t>(warp)) continue;  // the other consumer's page
             mbar_wait(&full[warp], (n >> 1) & 1);
@@ -245,26 +246,36 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tkv, const DmArgs g) 
         }
         named_bar_sync(1, 64);
         if (warp == 0 && gq == 0) {
+            // The item's pages alternate between the two consumers starting with whichever owns the current ring stage, so
+            // WHICH warp holds the state of pages p0, p0+2, … depends on the CTA's history.  The merge is written in terms of
+            // (first-page state A, second-page state B) with a fixed operation order, so that the result of an item does not
+            // depend on where in a CTA's stream it ran (a sequence gives bit-identical output wherever it sits in the batch).
             const float m1 = mb[HD], l1 = mb[HD + 1];
-            const float M = fmaxf(m_run, m1);
-            const float a0 = (m_run == -INFINITY) ? 0.f : exp2f((m_run - M) * g.scale_log2);
-            const float a1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - M) * g.scale_log2);
-            const float L = l_run * a0 + l1 * a1;
+            const float mA = w0_first ? m_run : m1, mB = w0_first ? m1 : m_run;
+            const float lA = w0_first ? l_run : l1, lB = w0_first ? l1 : l_run;
+            const float M = fmaxf(mA, mB);
+            const float aA = (mA == -INFINITY) ? 0.f : exp2f((mA - M) * g.scale_log2);
+            const float aB = (mB == -INFINITY) ? 0.f : exp2f((mB - M) * g.scale_log2);
+            const float L = fmaf(lB, aB, lA * aA);
             const long long base = static_cast<long long>(seq) * g.n_heads + head;
+            auto merged = [&](float x0, float x1) {               // x0: this warp's value, x1: warp 1's
+                const float xA = w0_first ? x0 : x1, xB = w0_first ? x1 : x0;
+                return fmaf(xB, aB, xA * aA);
+            };
             if (g.n_splits == 1) {
                 const float inv = 1.0f / L;
                 bf16* op = g.out + base * HD + 2 * tq;
 #pragma unroll
                 for (int dt = 0; dt < DT; ++dt) {
                     const float2 o1 = *reinterpret_cast<const float2*>(mb + dt * 8 + 2 * tq);
-                    *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16x2((o[dt][0] * a0 + o1.x * a1) * inv, (o[dt][1] * a0 + o1.y * a1) * inv);
+                    *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16x2(merged(o[dt][0], o1.x) * inv, merged(o[dt][1], o1.y) * inv);
                 }
             } else {
                 float* op = g.o_part + (base * g.n_splits + split) * HD + 2 * tq;
 #pragma unroll
                 for (int dt = 0; dt < DT; ++dt) {
                     const float2 o1 = *reinterpret_cast<const float2*>(mb + dt * 8 + 2 * tq);
-                    *reinterpret_cast<float2*>(op + dt * 8) = make_float2(o[dt][0] * a0 + o1.x * a1, o[dt][1] * a0 + o1.y * a1);
+                    *reinterpret_cast<float2*>(op + dt * 8) = make_float2(merged(o[dt][0], o1.x), merged(o[dt][1], o1.y));
                 }
                 if (tq == 0) {
                     float* ml = g.ml_part + (base * g.n_splits + split) * 2;

@@ -136,8 +136,9 @@ class TeoModel:
         l, ps = self.cfg.llama, self.cfg.kv_page_size
         if self._kv_pool is None or self._kv_pool.shape[1] < n_pages:
             self._kv_pool = None
-            self._kv_pool = torch.empty(l.num_hidden_layers, n_pages, 2, l.num_attention_heads, ps, l.head_dim,
-                                        dtype=torch.bfloat16, device=self.device)
+            alloc = torch.zeros if os.environ.get("TEO_KV_ZERO") == "1" else torch.empty      # zeros: debugging aid only
+            self._kv_pool = alloc(l.num_hidden_layers, n_pages, 2, l.num_attention_heads, ps, l.head_dim,
+                                  dtype=torch.bfloat16, device=self.device)
         for i in range(l.num_hidden_layers):
             self._llama_layers[i].kv_pages = self._kv_pool[i].data_ptr()
 
