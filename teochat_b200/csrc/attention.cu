@@ -1,18 +1,18 @@
-// Attention kernels of the hot path.
+// Attention kernels of the hot path that do NOT use tcgen05 — kept as the fallbacks / cross-checks of the tensor-core
+// versions (attention_tc.cu: flash_tc_kernel for the ViT and prefill; decode_attn_mma.cu: the decode step's kernel) and
+// for shapes those do not cover.
 //
-// (1) flash_fwd_kernel — variable-length multi-head attention for the ViT blocks (non-causal,
-//     257 tokens, head_dim 64) and the LLaMA prefill (causal, head_dim 128).  Online-softmax
-//     tiles of BLOCK_M queries × 64 keys; Q/K/V tiles staged with cp.async into XOR-swizzled
-//     shared memory, contractions on mma.sync m16n8k16 (bf16 in, fp32 accumulate).  About 4 % of
-//     the model FLOPs; a tcgen05 version is a later-round item.
+// (1) flash_fwd_kernel — variable-length multi-head attention (ViT: non-causal, 257 tokens, head_dim 64; LLaMA prefill:
+//     causal, head_dim 128).  Online-softmax tiles of BLOCK_M queries × 64 keys; Q/K/V tiles staged with cp.async into
+//     XOR-swizzled shared memory, contractions on mma.sync m16n8k16 (bf16 in, fp32 accumulate).  Selected with
+//     TEO_FLASH=mma; GPU tests compare flash_tc_kernel against it.
 //
-// (2) decode_attn_kernel — one query token per sequence over the paged KV cache.  Pure HBM
-//     streaming (0.5 MiB per cached token per sequence): each CTA owns one
-//     (sequence, head, KV split), pulls whole [page_size × head_dim] K and V page slices with
-//     cp.async.bulk (16 KiB contiguous at page_size 64, head_dim 128) into a double-buffered
-//     shared-memory ring signalled by mbarriers, and does the dot products on CUDA cores
-//     (MHA: one query row per KV head, nothing for tensor cores to reuse).  Split partials are
-//     merged by decode_combine_kernel.
+// (2) decode_attn_kernel / decode_attn_persist_kernel — one query token per sequence over the paged KV cache on CUDA
+//     cores.  Pure HBM streaming (0.5 MiB per cached token per sequence): whole [page_size × head_dim] K and V
+//     page slices arrive by cp.async.bulk (16 KiB contiguous at page_size 64, head_dim 128) into a shared-memory ring
+//     signalled by mbarriers; one CTA per (sequence, head, KV split), or persistent CTAs walking those items as one page
+//     stream.  Used for (head_dim, page_size) other than (128, 64), through teo_decode_attention (no handle), and with
+//     TEO_DEC_ATTN=cuda|v1.  Split partials of all decode kernels are merged by decode_combine_kernel.
 #include <stdlib.h>
 
 #include <cmath>

@@ -126,6 +126,31 @@ def test_generate_tiny_vs_live_oracle(tiny, tiny_oracle):
         assert (gl[0, s].float().cpu() - wl[s]).abs().max().item() <= LOGIT_RTOL * wl[s].abs().max().item(), s
 
 
+def test_generate_odd_widths_row_major_weights_vs_live_oracle():
+    """A config whose LLaMA MLP width (144) is a multiple of neither 32 nor 64: gate/up stay [gate; up] (SwiGLU as a kernel,
+    prefill and decode), the LLaMA weights stay row-major (2-D TMA maps) — the layouts a checkpoint with unusual widths gets."""
+    from oracle import model as OM
+    from oracle import weights as OW
+    cfg = TeoConfig.tiny()
+    cfg.llama.intermediate_size = 144
+    model = _model(cfg, 4242)
+    assert not model.w.gate_up_interleaved and not model.w.blocked["llama"]
+    sd = OW.make_state_dict(cfg, 4242)
+    ids = [1, 17, 99, -200, 5, 6, -200, 300, 301, 302]
+    frames = OW.synthetic_frames_u8(2, cfg.vision.image_size, 98)
+    px = OM.normalize_u8_nhwc(frames)
+    want, wl = OM.generate_greedy(sd, cfg, ids, px, 10, policy="bf16", return_logits=True)
+    got, gl = model.generate_batch([ids], frames_u8=[frames], max_new_tokens=10, return_logits=True)
+    top2 = wl.topk(2, -1).values
+    n = compare_tokens(got[0], want, (top2[:, 0] - top2[:, 1]).numpy(), wl.abs().amax(-1).numpy(), "odd widths")
+    assert n >= 1
+    for s in range(n):
+        assert (gl[0, s].float().cpu() - wl[s]).abs().max().item() <= LOGIT_RTOL * wl[s].abs().max().item(), s
+    assert model.generate_batch([ids], frames_u8=[frames], max_new_tokens=10) == got      # graph replay, same ids
+    del model
+    torch.cuda.empty_cache()
+
+
 def _full_width(depth_llama, depth_vit):
     cfg = TeoConfig.full()
     cfg.llama.num_hidden_layers = depth_llama
