@@ -250,9 +250,10 @@ def run_gpu(args):
     ms_e2e, gen_e2e, ph_e2e, _ = timed(host_list, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # launches: eager calls are counted by the handle; graph replays add (steps-2)·per-step launches
-    per_step = 1 + cfg.llama.num_hidden_layers * 14 + 5          # upper bound of kernels in one decode step
-    replays = sum(max(0, p["decode_steps"] - 1) for p in ph_dev) if model.use_graph else 0
+    # launches: eager calls are counted by the handle (teo_launch_count); a graph replay relaunches the kernels of one decode
+    # step, counted on the eager step that preceded the capture (fallback: the upper bound 14 per layer + 6)
+    per_step = model.decode_step_launches or (1 + cfg.llama.num_hidden_layers * 14 + 5)
+    replays = sum(p.get("graph_replays", 0) for p in ph_dev)
     gpu_launches = int(launches_eager + replays * per_step)
 
     roof = decode_attention_roofline(model, cfg, B, S0 + new // 2, dev) if not args.tiny else None

@@ -58,6 +58,7 @@ class TeoModel:
         self.use_graph = os.environ.get("TEO_NO_GRAPH", "0") != "1"
         self.set_pdl(os.environ.get("TEO_NO_PDL", "0") != "1")
         self.last_timings: Dict[str, float] = {}
+        self.decode_step_launches = 0          # counted on the eager step that precedes graph capture
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -345,7 +346,9 @@ class TeoModel:
         done = 0
         use_graph = self.use_graph and not return_logits
         if use_graph and st.graph is None and n_steps >= 5:
+            l0 = self.launch_count()
             step()                      # first step eagerly (warms function attributes / tensor maps), then capture once
+            self.decode_step_launches = self.launch_count() - l0       # kernels in one decode step (= one graph replay)
             done = 1
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
@@ -355,9 +358,11 @@ class TeoModel:
                 step()
             st.graph = graph
         graph = st.graph if use_graph else None
+        replays = 0
         while done < n_steps:
             if graph is not None:
                 graph.replay()
+                replays += 1
             else:
                 step()
                 if return_logits:
@@ -372,7 +377,7 @@ class TeoModel:
             torch.cuda.synchronize(dev)
             self.last_timings = {"vit_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
                                  "decode_ms": ev[2].elapsed_time(ev[3]), "frames": int(sum(per_sample)),
-                                 "prefill_tokens": T, "decode_steps": done, "batch": B}
+                                 "prefill_tokens": T, "decode_steps": done, "batch": B, "graph_replays": replays}
         outs: List[List[int]] = []
         for b in range(B):
             row = toks[b]
