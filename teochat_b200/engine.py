@@ -26,6 +26,24 @@ from .constants import IMAGE_TOKEN_INDEX
 from .weights import TeoWeights
 
 
+_NVTX_OK = True
+
+
+def _nvtx(push: Optional[str]) -> None:
+    """NVTX range per phase (vit / prefill / decode) for nsys / ncu timelines; a no-op cost without a profiler and switched off
+    for good if the NVTX bindings are unavailable."""
+    global _NVTX_OK
+    if not _NVTX_OK:
+        return
+    try:
+        if push is None:
+            torch.cuda.nvtx.range_pop()
+        else:
+            torch.cuda.nvtx.range_push(push)
+    except Exception:
+        _NVTX_OK = False
+
+
 def _cdiv(a: int, b: int) -> int:
     return (a + b - 1) // b
 
@@ -247,11 +265,14 @@ class TeoModel:
         if ev:
             ev[0].record()
         # ---- vision: all frames of the batch in one go
+        _nvtx("teo.vit+projector")
         per_sample = [int(x.shape[0]) for x in imgs]
         stacked = torch.cat([x.to(dev, non_blocking=True) for x in imgs], dim=0)
         proj = self.encode_images(frames_u8=stacked) if frames_u8 is not None else self.encode_images(pixel_values=stacked)
         if ev:
             ev[1].record()
+        _nvtx(None)
+        _nvtx("teo.prefill")
         # ---- splice plan (host integers) → device
         srcs, lens = self.plan_splice(input_ids, per_sample)
         T, max_len = int(sum(lens)), int(max(lens))
@@ -335,6 +356,8 @@ class TeoModel:
         if ev:
             ev[2].record()
 
+        _nvtx(None)
+        _nvtx("teo.decode")
         # ---- decode: one captured step, replayed (the graph is cached with the state above)
         def step():
             L.check(self.lib.teo_llama_decode_step(self._h, C.byref(self._llama), next_ids.data_ptr(), d_len.data_ptr(),
@@ -373,6 +396,7 @@ class TeoModel:
         if ev:
             ev[3].record()
         toks = tokens.cpu().numpy()
+        _nvtx(None)
         if ev:
             torch.cuda.synchronize(dev)
             self.last_timings = {"vit_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
