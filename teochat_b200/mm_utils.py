@@ -1,4 +1,4 @@
-"""Host-side token utilities of the hot path (mirror of videollava/mm_utils.py:43-104)."""
+"""Host-side token / image utilities of the hot path (mirror of videollava/mm_utils.py:10-104)."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -29,6 +29,40 @@ def tokenizer_image_token(prompt: str, tokenizer, image_token_index: int = IMAGE
     if return_tensors == "pt":
         return torch.tensor(ids, dtype=torch.long)
     raise ValueError(f"Unsupported tensor type: {return_tensors}")
+
+
+def load_image_from_base64(image):
+    """mm_utils.py:10-11."""
+    import base64
+    from io import BytesIO
+
+    from PIL import Image
+    return Image.open(BytesIO(base64.b64decode(image)))
+
+
+def expand2square(pil_img, background_color):
+    """Pad a PIL image to a square on a ``background_color`` canvas, the picture centred along its short side with the odd
+    pixel after it (mm_utils.py:14-25; used when ``image_aspect_ratio == 'pad'``)."""
+    from PIL import Image
+    w, h = pil_img.size
+    if w == h:
+        return pil_img
+    side = max(w, h)
+    canvas = Image.new(pil_img.mode, (side, side), background_color)
+    canvas.paste(pil_img, ((side - w) // 2, (side - h) // 2))
+    return canvas
+
+
+def process_images(images, image_processor, model_cfg):
+    """mm_utils.py:28-40: with ``model_cfg.image_aspect_ratio == 'pad'`` every image is squared on the processor's mean colour and
+    preprocessed on its own (stacked when the shapes agree); otherwise the processor takes the whole list."""
+    if getattr(model_cfg, "image_aspect_ratio", None) != "pad":
+        return image_processor(images, return_tensors="pt")["pixel_values"]
+    fill = tuple(int(c * 255) for c in image_processor.image_mean)
+    out = [image_processor.preprocess(expand2square(im, fill), return_tensors="pt")["pixel_values"][0] for im in images]
+    if all(x.shape == out[0].shape for x in out):
+        return torch.stack(out, dim=0)
+    return out
 
 
 def get_model_name_from_path(model_path: str) -> str:

@@ -81,6 +81,40 @@ def test_misc_helpers():
     assert extract_bboxes("see [1, 2, 30, 40] and [5, 6, 7, 8]") == [[1, 2, 30, 40], [5, 6, 7, 8]]
 
 
+def test_expand2square_and_process_images():
+    """mm_utils.py:14-40 — checked against an independent numpy formulation of the padding."""
+    import base64
+    from io import BytesIO
+    from types import SimpleNamespace
+
+    from PIL import Image
+
+    from teochat_b200.mm_utils import expand2square, load_image_from_base64, process_images
+    rng = np.random.RandomState(1)
+    fill = (122, 116, 104)
+    for h, w in [(40, 40), (40, 57), (61, 30)]:
+        arr = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        sq = np.asarray(expand2square(Image.fromarray(arr), fill))
+        side = max(h, w)
+        want = np.empty((side, side, 3), np.uint8)
+        want[:] = fill
+        top, left = (side - h) // 2, (side - w) // 2
+        want[top:top + h, left:left + w] = arr
+        assert sq.shape == (side, side, 3) and np.array_equal(sq, want)
+    p = TeoImageProcessor()
+    imgs = [Image.fromarray(rng.randint(0, 256, (100, 150, 3), dtype=np.uint8)), Image.fromarray(rng.randint(0, 256, (224, 224, 3), dtype=np.uint8))]
+    plain = process_images(imgs, p, SimpleNamespace())
+    assert plain.shape == (2, 3, 224, 224) and torch.equal(plain[1], p.preprocess(imgs[1])["pixel_values"][0])
+    padded = process_images(imgs, p, SimpleNamespace(image_aspect_ratio="pad"))
+    mean_fill = tuple(int(c * 255) for c in p.image_mean)
+    assert padded.shape == (2, 3, 224, 224)
+    assert torch.equal(padded[0], p.preprocess(expand2square(imgs[0], mean_fill))["pixel_values"][0])
+    assert not torch.equal(padded[0], plain[0]) and torch.equal(padded[1], plain[1])      # the square image is untouched
+    buf = BytesIO()
+    imgs[1].save(buf, format="PNG")
+    assert np.array_equal(np.asarray(load_image_from_base64(base64.b64encode(buf.getvalue()))), np.asarray(imgs[1]))
+
+
 def test_processor_matches_torchvision():
     from PIL import Image
     from torchvision import transforms
