@@ -240,6 +240,18 @@ def main():
             arrays[f"margin_{ci}"] = (top2[:, 0] - top2[:, 1]).numpy()
             print(f"case {ci}: prompt {len(prompt)} chars, ids {len(ids)}, S0 {t['inputs_embeds'].shape[1]}, {new} new tokens "
                   f"{arrays[f'tokens_{ci}'].tolist()} → {out!r}; min top-2 margin {arrays[f'margin_{ci}'].min():.3g}", flush=True)
+        # quirk 4 (llava_arch.py:296-299): the spliced sequence is cut at config.tokenizer_model_max_length — the reference's
+        # own prepare_inputs_labels_for_multimodal on case 1 (306 positions) with the attribute set to 200
+        model.config.tokenizer_model_max_length = 200
+        px = torch.from_numpy(arrays["pixel_values_f16_1"]).float()
+        with torch.no_grad():
+            _, _, _, _, emb, _ = model.prepare_inputs_labels_for_multimodal(torch.from_numpy(arrays["input_ids_1"])[None], None, None, None,
+                                                                           None, [im for im in px])
+        model.config.tokenizer_model_max_length = None
+        meta["truncation"] = {"case": 1, "tokenizer_model_max_length": 200}
+        arrays["trunc_embeds_shape"] = np.asarray(emb.shape, dtype=np.int64)
+        arrays["trunc_inputs_embeds"] = emb.flatten()[::STRIDE].numpy()
+        print("truncation: inputs_embeds", tuple(emb.shape), flush=True)
     np.savez_compressed(os.path.join(HERE, "reference_path.npz"), **arrays)
     with open(os.path.join(HERE, "reference_path.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -66,3 +66,22 @@ def test_oracle_equals_reference_tower_projector_splice_and_tokens(ref):
         want = arrays[f"logits_{ci}"]
         assert toks == arrays[f"tokens_{ci}"].tolist()
         assert np.abs(logits.numpy() - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_splice_truncation_equals_reference(ref):
+    """the reference's prepare_inputs_labels_for_multimodal cuts the spliced sequence at
+    config.tokenizer_model_max_length (llava_arch.py:296-299) — after the image features have been spliced in."""
+    import copy
+    cfg, meta, arrays, sd = ref
+    t = meta["truncation"]
+    ci, st = t["case"], meta["stride"]
+    cfg2 = copy.deepcopy(cfg)
+    cfg2.tokenizer_model_max_length = t["tokenizer_model_max_length"]
+    px = torch.from_numpy(arrays[f"pixel_values_f16_{ci}"]).float()
+    emb = OM.splice(sd, cfg2, arrays[f"input_ids_{ci}"].tolist(), OM.encode_images(sd, cfg2, px))
+    assert [1, *emb.shape] == arrays["trunc_embeds_shape"].tolist() == [1, t["tokenizer_model_max_length"], cfg.llama.hidden_size]
+    want = arrays["trunc_inputs_embeds"]
+    assert np.abs(emb.flatten()[::st].numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    # and it is a prefix of the untruncated splice
+    full = arrays[f"inputs_embeds_{ci}"]
+    assert arrays[f"embeds_shape_{ci}"][1] > t["tokenizer_model_max_length"] and full.shape[0] > want.shape[0]
