@@ -85,3 +85,37 @@ def test_splice_truncation_equals_reference(ref):
     # and it is a prefix of the untruncated splice
     full = arrays[f"inputs_embeds_{ci}"]
     assert arrays[f"embeds_shape_{ci}"][1] > t["tokenizer_model_max_length"] and full.shape[0] > want.shape[0]
+
+
+def test_product_splice_plan_reproduces_reference_embeds(ref):
+    """The product's integer splice plan (TeoModel.plan_splice — pure host code, called here without a GPU) gathers exactly
+    the rows the reference's prepare_inputs_labels_for_multimodal concatenates: applying the plan to the oracle's embedding table
+    and projector output gives the reference's inputs_embeds, for every fixture case, ragged in one batch, and truncated."""
+    import copy
+    from types import SimpleNamespace
+
+    from teochat_b200.engine import TeoModel
+    cfg, meta, arrays, sd = ref
+    st = meta["stride"]
+    E = sd["model.embed_tokens.weight"].float()
+    ids_all = [arrays[f"input_ids_{ci}"].tolist() for ci in range(len(meta["cases"]))]
+    n_img = [len(c["images"]) for c in meta["cases"]]
+    feats = torch.cat([OM.encode_images(sd, cfg, torch.from_numpy(arrays[f"pixel_values_f16_{ci}"]).float()) for ci in range(len(ids_all))])
+    flat = feats.reshape(-1, cfg.llama.hidden_size)                 # [all frames * 256, h]: the plan's image rows index this
+    srcs, lens = TeoModel.plan_splice(SimpleNamespace(cfg=cfg), ids_all, n_img)
+    for ci, (src, n) in enumerate(zip(srcs, lens)):
+        assert [1, n, cfg.llama.hidden_size] == arrays[f"embeds_shape_{ci}"].tolist()
+        src = torch.from_numpy(src)
+        emb = torch.where((src >= 0)[:, None], E[src.clamp_min(0)], flat[(-(src + 1)).clamp_min(0)])
+        want = arrays[f"inputs_embeds_{ci}"]
+        assert np.abs(emb.flatten()[::st].numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    t = meta["truncation"]
+    cfg2 = copy.deepcopy(cfg)
+    cfg2.tokenizer_model_max_length = t["tokenizer_model_max_length"]
+    srcs, lens = TeoModel.plan_splice(SimpleNamespace(cfg=cfg2), [ids_all[t["case"]]], [n_img[t["case"]]])
+    assert lens == [t["tokenizer_model_max_length"]]
+    src = torch.from_numpy(srcs[0])
+    one = OM.encode_images(sd, cfg, torch.from_numpy(arrays[f"pixel_values_f16_{t['case']}"]).float()).reshape(-1, cfg.llama.hidden_size)
+    emb = torch.where((src >= 0)[:, None], E[src.clamp_min(0)], one[(-(src + 1)).clamp_min(0)])
+    want = arrays["trunc_inputs_embeds"]
+    assert np.abs(emb.flatten()[::st].numpy() - want).max() <= 2e-5 * np.abs(want).max()
