@@ -184,6 +184,24 @@ int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed)
  * prologue and — for the GEMMs — weight prefetch overlap the tail of its predecessor.  Results are identical. */
 int teo_set_pdl(teo_handle* h, int enabled);
 
+/* ---- Exact (parity) mode ---------------------------------------------------------------- */
+/* The north-star parity clause asks for bit-exact greedy ids "with fp32 accumulation".  With bf16 activation storage a
+ * 32-layer random-init LLaMA sits 3-4 % from an fp32 run whatever the kernels do, so the whole-model entry points below
+ * have a second mode, selected per model struct (`exact != 0`): activations, residual stream and KV pages are f32 in
+ * HBM; every nn.Linear still runs on the tensor cores, its f32 input split into three bf16 terms (hi + mid + lo == x)
+ * that are contracted against the same bf16 weights with fp32 accumulation (teo_gemm_bf16x3); norms, RoPE, softmax and
+ * activations run in fp32 with the HF-4.31 op order.  Buffers that change type: teo_vit_encode feats f32;
+ * teo_projector_mlp2x feats/out f32; teo_llama_prefill x f32 (build it with teo_splice_embed_f32); kv_pages f32
+ * [n_pages][2][n_heads][page_size][head_dim].  The *_workspace_bytes queries follow the struct's flag. */
+int teo_splice_embed_f32(const void* embed_tokens, const void* image_feats_f32, const void* src, void* out_f32, int tokens,
+                         int d, void* stream);
+/* x f32 [rows,K] -> bf16 [rows,3K] = hi | mid | lo planes (K % 4 == 0) */
+int teo_split_f32_bf16x3(const void* x_f32, void* planes_bf16, int rows, int K, void* stream);
+/* C f32 [M,N] = X[M,K]·W[N,K]^T + bias[N] (+ residual f32 [M,N], may alias C); X as the planes above (K % 64 == 0);
+ * W bf16 row-major [N,K] or blocked (w_blocked != 0).  Workspace: teo_gemm_workspace_bytes(M, N, 3*K). */
+int teo_gemm_bf16x3(teo_handle* h, const void* planes_bf16, const void* W, int w_blocked, void* C_f32, int M, int N, int K,
+                    const void* bias, const void* residual_f32, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole-model entry points ---------------------------------------------------------- */
 typedef struct {
     const void *ln1_w, *ln1_b;   /* [d] */
@@ -198,6 +216,7 @@ typedef struct {
     int hidden, inter, heads, image, patch, kpad, act, layers_run;
     float eps;
     int w_blocked;               /* != 0: every GEMM weight below is in the blocked layout (teo_weight_to_blocked) */
+    int exact;                   /* != 0: exact (parity) mode, see "Exact mode" below: feats is f32 */
     const void* patch_w;         /* [hidden, kpad] bf16, columns (c*P+ky)*P+kx, zero padded */
     const void *cls, *pos;       /* [hidden], [np+1, hidden] */
     const void *pre_ln_w, *pre_ln_b;
@@ -215,6 +234,7 @@ int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void* frames_u8,
 typedef struct {
     int in_dim, hidden;
     int w_blocked;       /* != 0: w0 / w2 in the blocked layout */
+    int exact;           /* != 0: exact mode — feats and out are f32 */
     const void *w0, *b0; /* [hidden, in_dim], [hidden] */
     const void *w2, *b2; /* [hidden, hidden], [hidden] */
 } teo_projector;
@@ -239,6 +259,7 @@ typedef struct {
     int w_blocked;                   /* != 0: qkv_w / o_w / gate_up_w / down_w / lm_head in the blocked layout (embed stays row-major) */
     int gate_up_interleaved;         /* != 0: gate_up_w rows interleaved in blocks of 32 (TEO_ACT_SWIGLU_PAIRS), inter % 32 == 0;
                                         0: gate rows then up rows */
+    int exact;                       /* != 0: exact mode — x (prefill) is f32 [tokens,h] and every layer's kv_pages pool is f32 */
     const void *rope_cos, *rope_sin; /* f32 [rope_max_pos, head_dim/2] */
     const void* embed;      /* [vocab, h] */
     const void* final_norm; /* [h] */

@@ -124,6 +124,9 @@ struct GemmEpilogue {
     int ldr = 0;
     int act = TEO_ACT_NONE;
     int out_fp32 = 0;                 // C is float instead of bf16
+    int residual_f32 = 0;             // residual is float [M, ldr] (needs out_fp32; may alias C)
+    int k_planes = 1;                 // exact mode: A is [M, k_planes·K] — an fp32 activation split into k_planes bf16 terms
+                                      // (hi | mid | lo) stored side by side; every plane is multiplied by the same W[N,K]
 };
 
 // C[M,N] = epilogue(A[M,K] · W[N,K]^T).  Chooses the swap-AB / split-K schedule for small M.

@@ -148,10 +148,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             uint32_t ph = 0;
             // operand loads: weights may live in the blocked layout (contiguous 16 KiB tiles → full-rate HBM bursts)
             auto load_a = [&](int st, int kb, int m_blk) {
+                if (g.w_is_a && g.k_wrap) kb %= g.k_wrap;
                 if (g.w_is_a && g.w_blocked) tma_load_4d(smem_a + st * A_STAGE_BYTES, &tma_a, &full_bar[st], 0, 0, kb, m_blk);
                 else tma_load_2d(smem_a + st * A_STAGE_BYTES, &tma_a, &full_bar[st], kb * BK, m_blk * BM);
             };
             auto load_b = [&](int st, int kb, int n_blk) {
+                if (!g.w_is_a && g.k_wrap) kb %= g.k_wrap;
                 if (!g.w_is_a && g.w_blocked) tma_load_4d(smem_b + st * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[st], 0, 0, kb, n_blk * (BN / 128));
                 else tma_load_2d(smem_b + st * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[st], kb * BK, n_blk * BN);
             };
@@ -312,7 +314,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
                                 }
-                                if (g.residual) {
+                                if (g.residual && g.residual_f32) {
+                                    const float* rp = reinterpret_cast<const float*>(g.residual) + static_cast<long long>(m) * g.ldr + n0 + j0;
+                                    const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
+                                    x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+                                    x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+                                } else if (g.residual) {
                                     const uint4 rv = *reinterpret_cast<const uint4*>(g.residual + static_cast<long long>(m) * g.ldr + n0 + j0);
                                     const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
@@ -348,7 +355,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
 // out[r,c] = act(Σ_slots partial[slot][r,c] + bias[c]) + residual[r,c] — fixed summation order (deterministic).
 __global__ void splitk_reduce_kernel(PartialInfo pi, void* out, long long ldo, const bf16* __restrict__ bias,
-                                     const bf16* __restrict__ residual, long long ldr, int act, int out_fp32, int rows, int cols) {
+                                     const bf16* residual, long long ldr, int act, int out_fp32, int res_f32, int rows, int cols) {
     pdl_trigger();
     pdl_wait();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -359,7 +366,7 @@ __global__ void splitk_reduce_kernel(PartialInfo pi, void* out, long long ldo, c
     for (int s = 0; s < n; ++s) acc += pi.P[s * pi.stride + i];
     if (bias) acc += __bfloat162float(bias[c]);
     acc = apply_act(acc, act);
-    if (residual) acc += __bfloat162float(residual[r * ldr + c]);
+    if (residual) acc += res_f32 ? reinterpret_cast<const float*>(residual)[r * ldr + c] : __bfloat162float(residual[r * ldr + c]);
     if (out_fp32) reinterpret_cast<float*>(out)[r * ldo + c] = acc;
     else reinterpret_cast<bf16*>(out)[r * ldo + c] = __float2bfloat16_rn(acc);
 }
@@ -574,6 +581,12 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     TEO_CHECK_ARG(ldc % (ep.out_fp32 ? 4 : 8) == 0, "gemm: ldc (%d) breaks 16-byte row alignment", ldc);
     TEO_CHECK_ARG(ep.residual == nullptr || ep.ldr % 8 == 0, "gemm: ldr (%d) must be a multiple of 8", ep.ldr);
     TEO_CHECK_ARG((reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: C not 16-byte aligned");
+    TEO_CHECK_ARG(ep.k_planes >= 1 && ep.k_planes <= 3 && (ep.k_planes == 1 || (K % BK == 0 && ep.out_fp32)),
+                  "gemm: split operands (k_planes=%d) need K %% 64 == 0 and fp32 output", ep.k_planes);
+    TEO_CHECK_ARG(!ep.residual_f32 || (ep.out_fp32 && ep.ldr % 4 == 0), "gemm: an fp32 residual needs fp32 output and ldr %% 4 == 0");
+    const int Kw = K;                 // columns of W
+    K *= ep.k_planes;                 // contraction length seen by the kernel (= columns of A)
+    TEO_CHECK_ARG(lda >= K, "gemm: lda (%d) smaller than k_planes * K (%d)", lda, K);
     TEO_CHECK_ARG(ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0, "gemm: bias not 16-byte aligned");
     TEO_CHECK_ARG(ep.residual == nullptr || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0,
                   "gemm: residual not 16-byte aligned");
@@ -593,6 +606,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     g.bias = ep.bias;
     g.residual = ep.residual;
     g.ldr = ep.ldr;
+    g.residual_f32 = ep.residual_f32;
+    g.k_wrap = ep.k_planes > 1 ? Kw / BK : 0;
     g.C = C;
     g.ldc = ldc;
     g.K = K;
@@ -603,8 +618,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
             g.N = M;
         g.transposed = 1;
         g.w_blocked = w_blocked ? 1 : 0;
-        if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));
-        else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &ta));
+        if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, Kw, 1, &ta));
+        else TEO_TRY(get_tmap_bf16(h, W, N, Kw, ldw, BM, &ta));
         TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
         {
             const size_t need = static_cast<size_t>(p.sk_smax) * M * N * sizeof(float);
@@ -627,8 +642,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
             // large tiled GEMM with bf16 output: the CTA-pair kernel (gemm_pair.cu), 256 x 256 tiles, each CTA loads 128 W rows
             g.w_blocked = w_blocked ? 1 : 0;
             g.tma_epi = 1;
-            if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &tb));
-            else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, BM, &tb));
+            if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, Kw, 1, &tb));
+            else TEO_TRY(get_tmap_bf16(h, W, N, Kw, ldw, BM, &tb));
             TEO_TRY(get_tmap_bf16(h, C, M, ep.act == TEO_ACT_SWIGLU_PAIRS ? N / 2 : N, ldc, 32, &tc));
             tr = tc;
             if (ep.residual) TEO_TRY(get_tmap_bf16(h, ep.residual, M, N, ep.ldr, 32, &tr));
@@ -636,8 +651,8 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         }
         g.w_blocked = (w_blocked && p.bn >= 128) ? 1 : 0;
         TEO_CHECK_ARG(!w_blocked || p.bn >= 128, "gemm: blocked weights need N >= 128");
-        if (g.w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, p.bn / 128, &tb));
-        else TEO_TRY(get_tmap_bf16(h, W, N, K, ldw, p.bn, &tb));
+        if (g.w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, Kw, p.bn / 128, &tb));
+        else TEO_TRY(get_tmap_bf16(h, W, N, Kw, ldw, p.bn, &tb));
         if (!ep.out_fp32) {           // staged TMA-store epilogue: 32-row × 64-column boxes of C (and of the residual)
             g.tma_epi = 1;
             TEO_TRY(get_tmap_bf16(h, C, M, ep.act == TEO_ACT_SWIGLU_PAIRS ? N / 2 : N, ldc, 32, &tc));
@@ -661,7 +676,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         const int blocks = static_cast<int>((total + threads - 1) / threads);
         PartialInfo pi{reinterpret_cast<const float*>(workspace), total, (K + BK - 1) / BK, p.sk_q, p.sk_grid};
         TEO_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, pi, C, static_cast<long long>(ldc), ep.bias, ep.residual,
-                          static_cast<long long>(ep.ldr), ep.act, ep.out_fp32, M, N));
+                          static_cast<long long>(ep.ldr), ep.act, ep.out_fp32, ep.residual_f32, M, N));
         TEO_LAUNCH_CHECK("splitk_reduce_kernel");
         h->launches++;
     }

@@ -41,7 +41,9 @@ __global__ void init_u8_hash_kernel(uint8_t* out, size_t n, uint64_t seed) {
 // ------------------------------------------------------------------------------ patchify
 // One block per (frame, patch row): stage the P image rows in shared memory with coalesced loads,
 // then emit g patches × kpad bf16 columns, column index (c*P + ky)*P + kx.
-template <bool U8>
+// PLANES = 3 (exact mode, exact.cu): every value is written as three bf16 terms hi | mid | lo, kpad columns apart, in rows
+// of 3·kpad — the split-operand form of the exact-mode GEMM.
+template <bool U8, int PLANES>
 __global__ void patchify_kernel(const void* __restrict__ in, bf16* __restrict__ patches, int image, int patch, int kpad) {
     extern __shared__ float tile[];   // [3][P][image] normalised values
     const int g = image / patch;
@@ -65,7 +67,7 @@ __global__ void patchify_kernel(const void* __restrict__ in, bf16* __restrict__ 
     }
     __syncthreads();
     const int pdim = 3 * patch * patch;
-    bf16* dst = patches + (static_cast<size_t>(frame) * g * g + static_cast<size_t>(py) * g) * kpad;
+    bf16* dst = patches + (static_cast<size_t>(frame) * g * g + static_cast<size_t>(py) * g) * kpad * PLANES;
     for (int i = threadIdx.x; i < g * kpad; i += blockDim.x) {
         const int px = i / kpad, col = i % kpad;
         float v = 0.f;
@@ -73,7 +75,16 @@ __global__ void patchify_kernel(const void* __restrict__ in, bf16* __restrict__ 
             const int c = col / (patch * patch), r = col % (patch * patch), ky = r / patch, kx = r % patch;
             v = tile[(c * patch + ky) * image + px * patch + kx];
         }
-        dst[static_cast<size_t>(px) * kpad + col] = __float2bfloat16_rn(v);
+        bf16* o = dst + static_cast<size_t>(px) * kpad * PLANES + col;
+        const bf16 hi = __float2bfloat16_rn(v);
+        o[0] = hi;
+        if constexpr (PLANES == 3) {
+            float r = v - __bfloat162float(hi);
+            const bf16 mid = __float2bfloat16_rn(r);
+            r -= __bfloat162float(mid);
+            o[kpad] = mid;
+            o[2 * kpad] = __float2bfloat16_rn(r);
+        }
     }
 }
 
@@ -736,7 +747,7 @@ extern "C" int teo_init_u8_hash(void* out, size_t n, uint64_t seed, void* stream
     return TEO_OK;
 }
 
-static int patchify_common(bool u8, const void* in, void* patches, int n_frames, int image, int patch, int kpad, void* stream) {
+static int patchify_common(bool u8, const void* in, void* patches, int n_frames, int image, int patch, int kpad, void* stream, int planes = 1) {
     TEO_CHECK_ARG(in && patches, "patchify: null pointer");
     TEO_CHECK_ARG(n_frames > 0 && image > 0 && patch > 0 && image % patch == 0, "patchify: bad geometry image=%d patch=%d", image, patch);
     TEO_CHECK_ARG(kpad >= 3 * patch * patch && kpad % 8 == 0, "patchify: kpad=%d must be >= %d and a multiple of 8", kpad, 3 * patch * patch);
@@ -744,8 +755,13 @@ static int patchify_common(bool u8, const void* in, void* patches, int n_frames,
     const size_t smem = static_cast<size_t>(3) * patch * image * sizeof(float);
     TEO_CHECK_ARG(smem <= 48 * 1024, "patchify: image row tile (%zu B) exceeds 48 KiB", smem);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (u8) patchify_kernel<true><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
-    else patchify_kernel<false><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+    if (planes == 3) {
+        if (u8) patchify_kernel<true, 3><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+        else patchify_kernel<false, 3><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+    } else {
+        if (u8) patchify_kernel<true, 1><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+        else patchify_kernel<false, 1><<<n_frames * g, 256, smem, s>>>(in, static_cast<bf16*>(patches), image, patch, kpad);
+    }
     TEO_LAUNCH_CHECK("patchify_kernel");
     return TEO_OK;
 }
@@ -755,6 +771,12 @@ extern "C" int teo_patchify_u8_nhwc(const void* frames_u8, void* patches, int n_
 extern "C" int teo_patchify_f32_nchw(const void* pixel_values, void* patches, int n_frames, int image, int patch, int kpad, void* stream) {
     return patchify_common(false, pixel_values, patches, n_frames, image, patch, kpad, stream);
 }
+namespace teo {
+// exact mode: patches bf16 [n*g*g, 3*kpad] (hi | mid | lo planes of the normalised fp32 pixel values)
+int x_patchify(bool u8, const void* in, void* patches3, int n_frames, int image, int patch, int kpad, cudaStream_t stream) {
+    return patchify_common(u8, in, patches3, n_frames, image, patch, kpad, stream, 3);
+}
+}  // namespace teo
 
 extern "C" int teo_vit_assemble_preln(const void* patch_out, const void* cls, const void* pos, const void* ln_w, const void* ln_b,
                                       void* hidden, int n_frames, int n_patches, int d, float eps, void* stream) {

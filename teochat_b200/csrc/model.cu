@@ -8,6 +8,7 @@
 
 #include <new>
 
+#include "arena.h"
 #include "common.h"
 
 namespace teo {
@@ -68,34 +69,31 @@ __global__ void fill_cu_seqlens_kernel(int* cu, int n, int len) {
     if (i <= n) cu[i] = i * len;
 }
 
-// bump allocator over the caller's workspace (256-byte aligned slices)
-struct Arena {
-    uint8_t* base;
-    size_t size, off = 0;
-    bool ok = true;
-    Arena(void* p, size_t n) : base(static_cast<uint8_t*>(p)), size(n) {}
-    template <typename T>
-    T* take(size_t count) {
-        const size_t bytes = (count * sizeof(T) + 255) & ~static_cast<size_t>(255);
-        if (base == nullptr || off + bytes > size) {
-            ok = false;
-            off += bytes;
-            return nullptr;
-        }
-        T* p = reinterpret_cast<T*>(base + off);
-        off += bytes;
-        return p;
-    }
-};
-static inline size_t al256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+}  // namespace teo
 
+namespace teo {
+// exact (parity) mode launch sequences, model_exact.cu
+size_t vit_exact_workspace_bytes(const teo_vit_model* m, int n);
+int vit_encode_exact(teo_handle* h, const teo_vit_model* m, const void* frames_u8, const void* pixel_values, int n, void* feats,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t projector_exact_workspace_bytes(const teo_projector* p, int rows);
+int projector_exact(teo_handle* h, const teo_projector* p, const void* feats, int rows, void* out, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+size_t llama_prefill_exact_workspace_bytes(const teo_llama_model* m, int tokens, int n_seqs);
+size_t llama_decode_exact_workspace_bytes(const teo_llama_model* m, int n_seqs);
+int llama_prefill_exact(teo_handle* h, const teo_llama_model* m, void* x, int tokens, const void* positions, const void* seq_ids,
+                        const void* last_rows, int n_seqs, int max_seqlen, const void* block_table, int max_pages, void* logits,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int llama_decode_step_exact(teo_handle* h, const teo_llama_model* m, void* next_ids, void* seq_lens, void* finished, void* tokens, int max_new,
+                            void* step_ptr, int n_seqs, int max_seq_len, const void* block_table, int max_pages, void* logits, int eos_id,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace teo
 
 using namespace teo;
 
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" const char* teo_last_error(void) { return g_err; }
-extern "C" int teo_abi_version(void) { return 2; }
+extern "C" int teo_abi_version(void) { return 3; }
 
 extern "C" int teo_create(int device_id, teo_handle** out) {
     TEO_CHECK_ARG(out != nullptr, "teo_create: null out");
@@ -167,6 +165,7 @@ static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patc
 
 extern "C" size_t teo_vit_workspace_bytes(const teo_vit_model* m, int n_frames) {
     if (!m || n_frames <= 0) return 0;
+    if (m->exact) return vit_exact_workspace_bytes(m, n_frames);
     return vit_ws_layout(m, n_frames, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -177,6 +176,7 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     TEO_CHECK_ARG(n_frames > 0, "vit_encode: n_frames=%d", n_frames);
     TEO_CHECK_ARG(m->hidden % m->heads == 0 && m->layers_run >= 0 && m->layers != nullptr, "vit_encode: bad model");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m->exact) return vit_encode_exact(h, m, frames_u8, pixel_values, n_frames, feats, workspace, workspace_bytes, stream);
     const int g = m->image / m->patch, np = g * g, d = m->hidden, hd = d / m->heads;
     const int rows = n_frames * (np + 1);
     Arena A(workspace, workspace_bytes);
@@ -237,6 +237,7 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
 // ------------------------------------------------------------------------------ projector
 extern "C" size_t teo_projector_workspace_bytes(const teo_projector* p, int rows) {
     if (!p || rows <= 0) return 0;
+    if (p->exact) return projector_exact_workspace_bytes(p, rows);
     return al256(static_cast<size_t>(rows) * p->hidden * sizeof(bf16)) + al256(teo_gemm_workspace_bytes(rows, p->hidden, p->hidden));
 }
 
@@ -245,6 +246,7 @@ extern "C" int teo_projector_mlp2x(teo_handle* h, const teo_projector* p, const 
     TEO_CHECK_ARG(h && p && feats && out, "projector: null pointer");
     TEO_CHECK_ARG(rows > 0, "projector: rows=%d", rows);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (p->exact) return projector_exact(h, p, feats, rows, out, workspace, workspace_bytes, stream);
     Arena A(workspace, workspace_bytes);
     bf16* mid = A.take<bf16>(static_cast<size_t>(rows) * p->hidden);
     const size_t gws = teo_gemm_workspace_bytes(rows, p->hidden, p->hidden);
@@ -292,6 +294,7 @@ static size_t prefill_ws_layout(const teo_llama_model* m, int T, int B, Arena& A
 }
 extern "C" size_t teo_llama_prefill_workspace_bytes(const teo_llama_model* m, int tokens, int n_seqs) {
     if (!m || tokens <= 0 || n_seqs <= 0) return 0;
+    if (m->exact) return llama_prefill_exact_workspace_bytes(m, tokens, n_seqs);
     Arena A(nullptr, 0);
     return prefill_ws_layout(m, tokens, n_seqs, A, nullptr);
 }
@@ -329,6 +332,9 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
     TEO_CHECK_ARG(tokens > 0 && n_seqs > 0 && max_seqlen > 0, "llama_prefill: bad sizes");
     TEO_CHECK_ARG(m->hidden % m->heads == 0 && m->layer != nullptr, "llama_prefill: bad model");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m->exact)
+        return llama_prefill_exact(h, m, x_, tokens, positions, seq_ids, last_rows, n_seqs, max_seqlen, block_table, max_pages, logits,
+                                   workspace, workspace_bytes, stream);
     bf16* x = static_cast<bf16*>(x_);
     const int hdim = m->hidden, hd = hdim / m->heads;
     Arena A(workspace, workspace_bytes);
@@ -404,6 +410,7 @@ static size_t decode_ws_layout(const teo_llama_model* m, int B, Arena& A, Decode
 extern "C" size_t teo_llama_decode_workspace_bytes(const teo_llama_model* m, int n_seqs, int max_seq_len) {
     (void)max_seq_len;
     if (!m || n_seqs <= 0) return 0;
+    if (m->exact) return llama_decode_exact_workspace_bytes(m, n_seqs);
     Arena A(nullptr, 0);
     return decode_ws_layout(m, n_seqs, A, nullptr);
 }
@@ -414,6 +421,9 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     TEO_CHECK_ARG(h && m && next_ids && seq_lens && finished && tokens && step_ptr && block_table && logits, "llama_decode_step: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && max_seq_len > 0 && max_new > 0, "llama_decode_step: bad sizes");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m->exact)
+        return llama_decode_step_exact(h, m, next_ids, seq_lens, finished, tokens, max_new, step_ptr, n_seqs, max_seq_len, block_table,
+                                       max_pages, logits, eos_id, workspace, workspace_bytes, stream);
     const int hdim = m->hidden, hd = hdim / m->heads;
     Arena A(workspace, workspace_bytes);
     DecodeWs w;

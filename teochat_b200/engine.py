@@ -54,7 +54,10 @@ class TeoModel:
 
     VIT_CHUNK_FRAMES = 512
 
-    def __init__(self, cfg: TeoConfig, weights: TeoWeights, device=None):
+    def __init__(self, cfg: TeoConfig, weights: TeoWeights, device=None, precision: Optional[str] = None):
+        """``precision``: "bf16" (default; bf16 activations / KV, the measured path) or "exact" — the parity mode of
+        include/teochat_b200.h ("Exact mode"): fp32 activations, residual stream and KV pages, split-bf16 tensor-core GEMMs
+        with fp32 accumulation; matches the fp32 oracle to ~1e-5 at full depth.  TEO_PRECISION overrides the default."""
         if not torch.cuda.is_available():
             raise L.TeoError("teochat_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.cfg = cfg
@@ -62,7 +65,11 @@ class TeoModel:
         self.device = torch.device(device if device is not None else "cuda:0")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.dtype = torch.bfloat16
+        precision = precision or os.environ.get("TEO_PRECISION", "bf16")
+        if precision not in ("bf16", "exact"):
+            raise ValueError(f"precision must be 'bf16' or 'exact', got {precision!r}")
+        self.exact = precision == "exact"
+        self.dtype = torch.float32 if self.exact else torch.bfloat16      # storage type of activations / KV pages
         self.w = weights
         self.lib = L.load()
         self.model = SimpleNamespace(video_tower=None)     # eval.py:31 sets model.model.video_tower = None
@@ -123,12 +130,12 @@ class TeoModel:
         self._vit = L.VitModel(hidden=v.hidden_size, inter=v.intermediate_size, heads=v.num_attention_heads,
                                image=v.image_size, patch=v.patch_size, kpad=self.w.kpad,
                                act=L.ACT_BY_NAME[v.hidden_act], layers_run=n_run, eps=v.layer_norm_eps,
-                               w_blocked=int(bool(self.w.blocked.get("vit"))),
+                               w_blocked=int(bool(self.w.blocked.get("vit"))), exact=int(self.exact),
                                patch_w=p("vit.patch_w"), cls=p("vit.cls"), pos=p("vit.pos"),
                                pre_ln_w=p("vit.pre_ln_w"), pre_ln_b=p("vit.pre_ln_b"), layers=self._vit_layers)
         if cfg.mm_projector_type != "mlp2x_gelu":
             raise ValueError(f"Unknown projector type: {cfg.mm_projector_type}")   # projector/builder.py:51
-        self._proj = L.Projector(in_dim=v.hidden_size, hidden=l.hidden_size, w_blocked=int(bool(self.w.blocked.get("proj"))),
+        self._proj = L.Projector(in_dim=v.hidden_size, hidden=l.hidden_size, w_blocked=int(bool(self.w.blocked.get("proj"))), exact=int(self.exact),
                                  w0=p("proj.w0"), b0=p("proj.b0"),
                                  w2=p("proj.w2"), b2=p("proj.b2"))
         # RoPE tables exactly as HF builds cos_cached/sin_cached (fp32, on the host)
@@ -146,7 +153,7 @@ class TeoModel:
                                    layers=l.num_hidden_layers, vocab=l.vocab_size, page_size=cfg.kv_page_size,
                                    rope_max_pos=self.rope_max_pos, eps=l.rms_norm_eps,
                                    w_blocked=int(bool(self.w.blocked.get("llama"))),
-                                   gate_up_interleaved=int(bool(getattr(self.w, "gate_up_interleaved", False))),
+                                   gate_up_interleaved=int(bool(getattr(self.w, "gate_up_interleaved", False))), exact=int(self.exact),
                                    rope_cos=self._rope_cos.data_ptr(), rope_sin=self._rope_sin.data_ptr(),
                                    embed=p("llama.embed"), final_norm=p("llama.final_norm"),
                                    lm_head=p("llama.lm_head"), layer=self._llama_layers)
@@ -157,7 +164,7 @@ class TeoModel:
             self._kv_pool = None
             alloc = torch.zeros if os.environ.get("TEO_KV_ZERO") == "1" else torch.empty      # zeros: debugging aid only
             self._kv_pool = alloc(l.num_hidden_layers, n_pages, 2, l.num_attention_heads, ps, l.head_dim,
-                                  dtype=torch.bfloat16, device=self.device)
+                                  dtype=self.dtype, device=self.device)
         for i in range(l.num_hidden_layers):
             self._llama_layers[i].kv_pages = self._kv_pool[i].data_ptr()
 
@@ -165,7 +172,7 @@ class TeoModel:
     def encode_images(self, frames_u8: Optional[torch.Tensor] = None, pixel_values: Optional[torch.Tensor] = None) -> torch.Tensor:
         """encode_images (llava_arch.py:137-140): tower (hidden_states[select_layer], CLS dropped)
         + projector.  frames_u8: u8 [n,H,W,3] on the device, or pixel_values: f32 [n,3,H,W]
-        (already normalised).  Returns bf16 [n, tokens_per_image, llama_hidden]."""
+        (already normalised).  Returns [n, tokens_per_image, llama_hidden] in the model's storage type (bf16; f32 in exact mode)."""
         cfg, v = self.cfg, self.cfg.vision
         if cfg.mm_vision_select_feature != "patch":
             raise ValueError(f"Unexpected select feature: {cfg.mm_vision_select_feature}")
@@ -181,13 +188,14 @@ class TeoModel:
             src = pixel_values.to(device=self.device, dtype=torch.float32)
         src = src.to(self.device).contiguous()
         n, npch, d, hl = src.shape[0], v.num_patches, v.hidden_size, cfg.llama.hidden_size
-        out = torch.empty(n, npch, hl, dtype=torch.bfloat16, device=self.device)
+        out = torch.empty(n, npch, hl, dtype=self.dtype, device=self.device)
+        esz = out.element_size()
         stream = self._stream()
         for s in range(0, n, self.VIT_CHUNK_FRAMES):
             c = min(self.VIT_CHUNK_FRAMES, n - s)
             wsb = self.lib.teo_vit_workspace_bytes(C.byref(self._vit), c)
             ws = self._ws("vit", wsb)
-            feats = self._ws("vit_feats", c * npch * d * 2)
+            feats = self._ws("vit_feats", c * npch * d * esz)
             chunk = src[s:s + c]
             L.check(self.lib.teo_vit_encode(self._h, C.byref(self._vit),
                                             chunk.data_ptr() if frames_u8 is not None else None,
@@ -337,9 +345,9 @@ class TeoModel:
         finished.zero_()
         tokens.fill_(-1)
         step_ptr.fill_(1)
-        x = self._ws("x", T * h * 2)
-        L.check(self.lib.teo_splice_embed(self.w.t["llama.embed"].data_ptr(), proj.data_ptr(), d_src.data_ptr(), x.data_ptr(), T, h,
-                                          stream), "teo_splice_embed")
+        x = self._ws("x", T * h * proj.element_size())
+        splice = self.lib.teo_splice_embed_f32 if self.exact else self.lib.teo_splice_embed
+        L.check(splice(self.w.t["llama.embed"].data_ptr(), proj.data_ptr(), d_src.data_ptr(), x.data_ptr(), T, h, stream), "teo_splice_embed")
         pwb = self.lib.teo_llama_prefill_workspace_bytes(C.byref(self._llama), T, B)
         pws = self._ws("prefill", pwb)
         L.check(self.lib.teo_llama_prefill(self._h, C.byref(self._llama), x.data_ptr(), T, d_cu.data_ptr(), d_pos.data_ptr(),

@@ -3,7 +3,7 @@
 
 Offline there is no checkpoint, tokenizer or network, so ``model_path`` selects
 a synthetic ("random-init") model: ``"teochat-synthetic"`` / ``"teochat-synthetic-tiny"``,
-optionally ``?seed=N``.  Like the reference's builder (builder.py:33) the model name must contain
+optionally ``?seed=N`` and ``&precision=exact`` (the fp32 parity mode).  Like the reference's builder (builder.py:33) the model name must contain
 ``llava`` or ``teochat``.  A directory path loads an HF-format checkpoint (merged, or a LoRA adapter over ``model_base``; a
 separate image-tower checkpoint directory may be given through ``cache_dir``) via teochat_b200.checkpoint.
 """
@@ -32,6 +32,8 @@ def load_model(model_path, model_base=None, load_8bit=False, load_4bit=False, ca
     if "llava" not in model_name.lower() and "teochat" not in model_name.lower():
         raise ValueError(f"model name {model_name!r} must contain 'llava' or 'teochat' (builder.py:33)")
     dev = torch.device(device if device is not None else "cuda:0")
+    opts = dict(kv.partition("=")[::2] for kv in filter(None, query.split("&")))
+    precision = opts.get("precision")                  # "exact": the fp32 parity mode (engine.TeoModel); default bf16
     if os.path.isdir(path):
         # HF-format directory: merged checkpoint, or LoRA adapter over `model_base` (builder.py:33-112)
         from .. import checkpoint as CK
@@ -39,18 +41,14 @@ def load_model(model_path, model_base=None, load_8bit=False, load_4bit=False, ca
         sd = CK.load_state_dict(path, model_base if (model_base and os.path.isdir(str(model_base))) else None, tower_path=cache_dir)
         weights = TeoWeights.from_state_dict(sd, cfg, dev)
         del sd
-        model = TeoModel(cfg, weights, dev)
+        model = TeoModel(cfg, weights, dev, precision=precision)
         model.model.video_tower = None
         return CK.load_tokenizer(model_base if (model_base and os.path.isdir(str(model_base))) else path, cfg.llama.vocab_size), model, \
             TeoImageProcessor(cfg.vision.image_size)
-    seed = 1234
-    for kv in filter(None, query.split("&")):
-        k, _, v = kv.partition("=")
-        if k == "seed":
-            seed = int(v)
+    seed = int(opts.get("seed", 1234))
     cfg = TeoConfig.tiny() if model_name.endswith("-tiny") else TeoConfig.full()
     weights = TeoWeights.from_synthetic(cfg, seed, dev)
-    model = TeoModel(cfg, weights, dev)
+    model = TeoModel(cfg, weights, dev, precision=precision)
     model.model.video_tower = None                     # eval.py:31
     tokenizer = StubTokenizer(cfg.llama.vocab_size)
     processor = TeoImageProcessor(cfg.vision.image_size)   # processor['image'] (eval.py:33)

@@ -30,12 +30,12 @@ class VitLayer(C.Structure):
 class VitModel(C.Structure):
     _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("image", C.c_int),
                 ("patch", C.c_int), ("kpad", C.c_int), ("act", C.c_int), ("layers_run", C.c_int),
-                ("eps", C.c_float), ("w_blocked", C.c_int), ("patch_w", vp), ("cls", vp), ("pos", vp), ("pre_ln_w", vp),
+                ("eps", C.c_float), ("w_blocked", C.c_int), ("exact", C.c_int), ("patch_w", vp), ("cls", vp), ("pos", vp), ("pre_ln_w", vp),
                 ("pre_ln_b", vp), ("layers", C.POINTER(VitLayer))]
 
 
 class Projector(C.Structure):
-    _fields_ = [("in_dim", C.c_int), ("hidden", C.c_int), ("w_blocked", C.c_int), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
+    _fields_ = [("in_dim", C.c_int), ("hidden", C.c_int), ("w_blocked", C.c_int), ("exact", C.c_int), ("w0", vp), ("b0", vp), ("w2", vp), ("b2", vp)]
 
 
 class LlamaLayer(C.Structure):
@@ -45,7 +45,7 @@ class LlamaLayer(C.Structure):
 class LlamaModel(C.Structure):
     _fields_ = [("hidden", C.c_int), ("inter", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
                 ("vocab", C.c_int), ("page_size", C.c_int), ("rope_max_pos", C.c_int), ("eps", C.c_float),
-                ("w_blocked", C.c_int), ("gate_up_interleaved", C.c_int), ("rope_cos", vp), ("rope_sin", vp), ("embed", vp),
+                ("w_blocked", C.c_int), ("gate_up_interleaved", C.c_int), ("exact", C.c_int), ("rope_cos", vp), ("rope_sin", vp), ("embed", vp),
                 ("final_norm", vp), ("lm_head", vp),
                 ("layer", C.POINTER(LlamaLayer))]
 
@@ -81,6 +81,9 @@ _SIGS = {
     "teo_rmsnorm": (i, [vp, vp, vp, i, i, f, vp]),
     "teo_swiglu": (i, [vp, vp, i, i, vp]),
     "teo_splice_embed": (i, [vp, vp, vp, vp, i, i, vp]),
+    "teo_splice_embed_f32": (i, [vp, vp, vp, vp, i, i, vp]),
+    "teo_split_f32_bf16x3": (i, [vp, vp, i, i, vp]),
+    "teo_gemm_bf16x3": (i, [vp, vp, vp, i, vp, i, i, i, vp, vp, vp, sz, vp]),
     "teo_argmax_step": (i, [vp, i, vp, vp, i, i, vp, i, i, vp]),
     "teo_sample_step": (i, [vp, i, f, i, u64, vp, vp, i, i, vp, i, i, vp]),
     "teo_set_sampling": (i, [vp, f, i, u64]),

@@ -32,21 +32,22 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/teochat_b200.h but not exported"
     assert set(syms) == set(L.EXPORTS), "ctypes signature table and header disagree"
-    assert lib.teo_abi_version() == 2
+    assert lib.teo_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     # pointer-sized fields, int fields in header order (catches drift between lib.py and the header)
     assert C.sizeof(L.VitLayer) == 12 * C.sizeof(C.c_void_p)
     assert C.sizeof(L.LlamaLayer) == 7 * C.sizeof(C.c_void_p)
-    assert [f for f, _ in L.VitModel._fields_][:10] == ["hidden", "inter", "heads", "image", "patch", "kpad", "act", "layers_run", "eps",
-                                                        "w_blocked"]
-    assert [f for f, _ in L.Projector._fields_][:3] == ["in_dim", "hidden", "w_blocked"]
-    assert [f for f, _ in L.LlamaModel._fields_][:12] == ["hidden", "inter", "heads", "layers", "vocab", "page_size", "rope_max_pos", "eps",
-                                                         "w_blocked", "gate_up_interleaved", "rope_cos", "rope_sin"]
+    assert [f for f, _ in L.VitModel._fields_][:11] == ["hidden", "inter", "heads", "image", "patch", "kpad", "act", "layers_run", "eps",
+                                                        "w_blocked", "exact"]
+    assert [f for f, _ in L.Projector._fields_][:4] == ["in_dim", "hidden", "w_blocked", "exact"]
+    assert [f for f, _ in L.LlamaModel._fields_][:13] == ["hidden", "inter", "heads", "layers", "vocab", "page_size", "rope_max_pos", "eps",
+                                                         "w_blocked", "gate_up_interleaved", "exact", "rope_cos", "rope_sin"]
     # field order in the header text itself
     hdr = open(os.path.join(ROOT, "include", "teochat_b200.h")).read()
-    for struct, fields in (("teo_vit_model", ["eps;", "w_blocked;", "patch_w;"]), ("teo_llama_model", ["eps;", "w_blocked;", "gate_up_interleaved;", "*rope_cos"])):
+    for struct, fields in (("teo_vit_model", ["eps;", "w_blocked;", "exact;", "patch_w;"]), ("teo_projector", ["w_blocked;", "exact;", "*w0"]),
+                           ("teo_llama_model", ["eps;", "w_blocked;", "gate_up_interleaved;", "exact;", "*rope_cos"])):
         body = hdr[hdr.rindex("typedef struct {", 0, hdr.index("} " + struct + ";")):hdr.index("} " + struct + ";")]
         pos = [body.index(f) for f in fields]
         assert pos == sorted(pos), struct
