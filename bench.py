@@ -1,15 +1,22 @@
 """Benchmark of the TEOChat inference hot path (contract in the task statement, §④).
 
-    python bench.py [--gpus N --steps K --warmup W]            this build on N B200s
-    python bench.py --impl reference [...]                    the CPU oracle port on the host cores
+    python bench.py [--gpus N --steps K --warmup W] [--config 1|2|4]     this build on N B200s
+    python bench.py --impl reference [...]                              the reference's CPU path on the host cores
 
 One "step" = one full pass of the hot path over one batch of synthetic input: ViT encode of all
-frames → projector → splice → ragged prefill → greedy decode of `new` tokens.  Workload at every
+frames → projector → splice → ragged prefill → greedy decode of `new` tokens.  The headline workload at every
 N is BASELINE.json configs[2] per GPU (T=8 frames, bs=32, 256 new tokens; configs[3] is the same
 per-GPU work on 8 GPUs): weak scaling, examples sharded across ranks, one NCCL all-gather of ids
 at the end.  `value` = generated tokens/s with the frames already resident in HBM; `e2e` = the
 same through the public batched API with frames in pinned HOST memory (H2D of the frames and D2H
-of the ids inside the timed region).
+of the ids inside the timed region).  At N=1 the line also carries `other_configs`: short measurements of configs[1]
+(T=1, bs=64, 128 new tokens) and of the per-GPU shape of configs[4] (T=16, bs=2 per GPU, 512 new tokens, 4k context);
+`--config 1|4` makes one of them the headline workload instead (e.g. configs[4] at its true bs=16 under torchrun on 8 GPUs).
+
+CPU legs (`--impl reference`, and `cpu_baseline` of the GPU line): BASELINE.json configs[0] — one 2-frame sequence, context
+≈ 580, greedy 16 tokens — end to end through the INSTALLED HF modules the way the reference drives them
+(oracle/hf_reference.py), fp32, all usable host cores.  It is a different (smaller) config than the GPU
+line and a port, not the reference package: both facts are in the line (`same_config`, `cpu_baseline.kind`).
 """
 import argparse
 import json
@@ -25,9 +32,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "generated_tokens_per_s"
 UNIT = "tokens/s"
-# CPU legs: one sequence, T=1 frame (context 317), 24 new tokens — context : new ≈ 13:1, close to the benchmark
-# config's 2130 : 256 ≈ 8:1, so the prefill / decode mix of the sample resembles the workload's (≈ 25 s here on 8 vCPUs)
-CPU_SAMPLE = (1, 24)
+# CPU legs: BASELINE.json configs[0] — one sequence of T=2 frames (context ≈ 580), greedy 16 tokens
+CPU_SAMPLE = (2, 16)
+# BASELINE.json configs → (frames T, examples per GPU, new tokens); configs[3] is configs[2] on 8 GPUs, configs[4] is bs=16 over 8 GPUs
+CONFIGS = {1: (1, 64, 128), 2: (8, 32, 256), 4: (16, 2, 512)}
 INSTRUCTION = ("This is a sequence of images captured at times: <video> "
                "What objects or changes can you see across the images?")
 
@@ -100,75 +108,161 @@ def host_cpus() -> int:
 
 
 def pick_cpu_threads() -> int:
-    """Thread count for the CPU leg: the candidate (powers of two up to the usable CPUs, TEO_CPU_THREADS overrides)
-    that runs a prefill-shaped fp32 matmul fastest.  Taking every visible core is not the fastest choice on a
-    many-socket host or under a cgroup quota (round 1: 32 threads on the GPU box ran 12x slower than 8 here)."""
-    import torch
+    """Fixed policy: every CPU this process may use (affinity mask ∩ cgroup quota, host_cpus()); TEO_CPU_THREADS overrides."""
     if os.environ.get("TEO_CPU_THREADS"):
         return max(1, int(os.environ["TEO_CPU_THREADS"]))
-    n = host_cpus()
-    cands = sorted({c for c in (4, 8, 16, 32, 64, 128) if c <= n} | {min(n, 128)})
-    a, b = torch.randn(512, 4096), torch.randn(4096, 4096)
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        a @ b
-        t0 = time.perf_counter()
-        for _ in range(3):
-            a @ b
-        t = time.perf_counter() - t0
-        if t < best_t * 0.95:                  # prefer fewer threads unless more is clearly faster
-            best, best_t = c, t
-    return best
+    return host_cpus()
 
 
-def cpu_reference_leg(n_frames: int, new_tokens: int, steps: int, warmup: int, seed: int = 1234):
-    """The oracle port (kind "port": the reference cannot be imported/compiled here) on all
-    host cores: fp32, random-init full-size weights, one sequence per step."""
+def cpu_reference_leg(n_frames: int, new_tokens: int, steps: int, warmup: int, seed: int = 1234, budget_s: float = None):
+    """BASELINE configs[0] through the installed HF modules (oracle/hf_reference.py; kind "port": the reference package
+    cannot be imported) on all usable host cores: fp32, random-init full-size weights, one sequence per step."""
     import torch
 
-    from oracle import model as OM
+    from oracle import hf_reference as HR
     from oracle import weights as OW
     from teochat_b200.config import TeoConfig
     cfg = TeoConfig.full()
     cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     sd = OW.make_state_dict(cfg, seed, dtype=torch.float32)
+    modules = HR.build_modules(cfg, sd)
     ids = make_prompt_ids(cfg, n_frames)
     frames = OW.synthetic_frames_u8(n_frames, cfg.vision.image_size, 11)
-    times = []
-    for it in range(warmup + steps):
+    times, phases = [], []
+    it = 0
+    while it < warmup + steps:
         t0 = time.perf_counter()
-        px = OM.normalize_u8_nhwc(frames)
-        toks = OM.generate_greedy(sd, cfg, ids, px, new_tokens, policy="fp32", eos_token_id=None)
+        toks, ph = HR.run_inference_greedy(modules, cfg, sd, ids, frames, new_tokens)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+            phases.append(ph)
+        if it == 0 and budget_s is not None and (warmup + steps) * dt > budget_s:
+            # a slow host: keep the whole run within the budget (>= 1 warm-up when any was asked for, >= 3 timed steps)
+            fit = max(3, int(budget_s / dt) - 1)
+            if warmup + steps > fit:
+                warmup = min(warmup, 1)
+                steps = max(3, min(steps, fit - warmup))
+        it += 1
     t = sum(times) / len(times)
-    s0 = len(ids) - n_frames + n_frames * cfg.tokens_per_image
+    mean = lambda k: sum(p[k] for p in phases) / len(phases)
     return {"value": new_tokens / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 sequence x T={n_frames} frame(s), context {s0}, {new_tokens} new tokens, fp32 oracle, "
+            "sample": f"BASELINE configs[0]: 1 sequence x T={n_frames} frames, context {phases[0]['context']}, greedy {new_tokens} new tokens, "
+                      f"installed HF CLIPVisionModel + LlamaForCausalLM (eager) fp32 driven like videollava.eval.inference; "
                       f"mean of {len(times)} run(s) after {warmup} warm-up",
-            "s_per_sample": t, "vit_frames_per_s": None}
+            "s_per_sample": t, "s_min": min(times), "s_max": max(times), "steps_run": len(times), "warmup_run": warmup,
+            "vit_frames_per_s": n_frames / mean("vision_s"), "prefill_tokens_per_s": phases[0]["context"] / mean("prefill_s"),
+            "decode_tokens_per_s": (new_tokens - 1) / mean("decode_s")}
+
+
+def workload_name(T, B, new, S0=None):
+    ctx = f", context {S0}" if S0 else ""
+    tag = {(1, 64, 128): "BASELINE configs[1]", (8, 32, 256): "BASELINE configs[2]/[3]", (16, 2, 512): "BASELINE configs[4] per-GPU shape"}.get((T, B, new), "custom")
+    return f"T={T} frames x bs={B} per GPU{ctx}, {new} new tokens, greedy ({tag})"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    T, new = CPU_SAMPLE                     # bounded sample per step (the full config would take hours on CPU)
-    cb = cpu_reference_leg(T, new, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["s_per_sample"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"T={args.frames} frames, bs={args.batch}/GPU, {args.new_tokens} new tokens (BASELINE configs[2]); "
-                                   "CPU arm timed on a bounded sample of it, see cpu_baseline.sample"},
+    T, new = CPU_SAMPLE                     # bounded sample per step: BASELINE configs[0] (the full GPU config would take hours on CPU)
+    cb = cpu_reference_leg(T, new, args.steps, args.warmup, budget_s=float(os.environ.get("TEO_CPU_BUDGET_S", "420")))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps_run"],
+            "warmup": cb["warmup_run"], "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": cb["s_per_sample"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "kind": cb["kind"], "same_config": False,
+            "config": {"workload": workload_name(args.frames, args.batch, args.new_tokens),
+                       "sample": "each step is BASELINE configs[0] (2 frames, context ~580, 16 new tokens, bs=1) on the host CPUs — NOT the GPU "
+                                 "arm's batch; see cpu_baseline.sample"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class Workload:
+    """One (T frames, B examples per GPU, new tokens) workload on this rank's replica: synthetic frames (device + pinned
+    host mirror), prompt ids, and the step function — generate_batch + the one collective (gather of the ids)."""
+
+    def __init__(self, model, cfg, rank, world, dev, T, B, new):
+        import ctypes as C
+
+        import torch
+
+        from teochat_b200 import lib as L
+        from teochat_b200.weights import tensor_seed
+        self.model, self.cfg, self.world, self.dev = model, cfg, world, dev
+        self.T, self.B, self.new = T, B, new
+        self.ids = [make_prompt_ids(cfg, T) for _ in range(B)]
+        self.S0 = len(self.ids[0]) - T + T * cfg.tokens_per_image
+        img = cfg.vision.image_size
+        # synthetic frames, distinct per rank/sample, generated on the device then mirrored to pinned host memory
+        frames_dev = torch.empty(B, T, img, img, 3, dtype=torch.uint8, device=dev)
+        L.check(model.lib.teo_init_u8_hash(frames_dev.data_ptr(), frames_dev.numel(), C.c_uint64(tensor_seed(1234 + rank + 1000 * T, "frames")),
+                                           torch.cuda.current_stream().cuda_stream))
+        self.frames_host = frames_dev.cpu().pin_memory()
+        self.dev_list = [frames_dev[b] for b in range(B)]
+        self.host_list = [self.frames_host[b] for b in range(B)]
+        self.n_total = B * world
+
+    def step(self, frames):
+        from teochat_b200 import dist as TD
+        outs = self.model.generate_batch(self.ids, frames_u8=frames, max_new_tokens=self.new, time_phases=True)
+        packed = TD.pack_tokens(outs, self.B, self.new, self.dev)
+        gathered = TD.gather_tokens(packed, self.n_total)          # the one collective (includes the D2H of the ids)
+        return outs, gathered
+
+    def sync_all(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def timed(self, frames, k):
+        """k steps bracketed by barrier + synchronize, CUDA events on the launching stream, MAX over ranks."""
+        import torch
+        import torch.distributed as dist
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = self.model.launch_count()
+        phases, gen = [], 0
+        e0.record()
+        for _ in range(k):
+            outs, _ = self.step(frames)
+            phases.append(dict(self.model.last_timings))
+            gen += sum(len(o) for o in outs)
+        e1.record()
+        self.sync_all()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            g = torch.tensor([gen], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            gen = int(g.item())
+        return ms, gen, phases, self.model.launch_count() - l0
+
+    def h2d_bytes(self):
+        B, S0 = self.B, self.S0
+        return int(self.frames_host.numel() + 4 * (3 * B * S0 + 3 * B + 1 + B * 64))
+
+    def summary(self, ms_dev, gen_dev, ph_dev, ms_e2e, gen_e2e, k):
+        """throughput figures of one measured workload (whole job: × world for the per-phase rates)."""
+        w = self.world
+        return {
+            "workload": workload_name(self.T, self.B, self.new, self.S0), "global_batch": self.n_total,
+            "value": gen_dev / (ms_dev / 1e3), "ms_per_step": ms_dev / k,
+            "e2e": {"value": gen_e2e / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": self.h2d_bytes(),
+                    "d2h_bytes_per_step": int(self.B * self.new * 4), "ms_per_step": ms_e2e / k},
+            "vit_frames_per_s": sum(p["frames"] for p in ph_dev) / (sum(p["vit_ms"] for p in ph_dev) / 1e3) * w,
+            "decode_tokens_per_s": sum(p["batch"] * p["decode_steps"] for p in ph_dev) / (sum(p["decode_ms"] for p in ph_dev) / 1e3) * w,
+            "prefill_tokens_per_s": sum(p["prefill_tokens"] for p in ph_dev) / (sum(p["prefill_ms"] for p in ph_dev) / 1e3) * w,
+            "phases_ms": {kk: sum(p[kk] for p in ph_dev) / k for kk in ("vit_ms", "prefill_ms", "decode_ms")},
+        }
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -176,10 +270,7 @@ def run_gpu(args):
     from teochat_b200 import dist as TD
     from teochat_b200.config import TeoConfig
     from teochat_b200.engine import TeoModel
-    from teochat_b200.weights import TeoWeights, tensor_seed
-    import ctypes as C
-
-    from teochat_b200 import lib as L
+    from teochat_b200.weights import TeoWeights
 
     rank, world, local = TD.init_from_env()
     dev = torch.device("cuda", local)
@@ -187,58 +278,15 @@ def run_gpu(args):
     cfg = TeoConfig.tiny() if args.tiny else TeoConfig.full()
     model = TeoModel(cfg, TeoWeights.from_synthetic(cfg, 1234, dev), dev)
     B, T, new = args.batch, args.frames, args.new_tokens
-    ids = [make_prompt_ids(cfg, T) for _ in range(B)]
-    S0 = len(ids[0]) - T + T * cfg.tokens_per_image
-    img = cfg.vision.image_size
-    # synthetic frames, distinct per rank/sample, generated on the device then mirrored to pinned host memory
-    frames_dev = torch.empty(B, T, img, img, 3, dtype=torch.uint8, device=dev)
-    L.check(model.lib.teo_init_u8_hash(frames_dev.data_ptr(), frames_dev.numel(), C.c_uint64(tensor_seed(1234 + rank, "frames")),
-                                       torch.cuda.current_stream().cuda_stream))
-    frames_host = frames_dev.cpu().pin_memory()
-    dev_list = [frames_dev[b] for b in range(B)]
-    host_list = [frames_host[b] for b in range(B)]
-    n_total = B * world
-
-    def step(frames):
-        outs = model.generate_batch(ids, frames_u8=frames, max_new_tokens=new, time_phases=True)
-        packed = TD.pack_tokens(outs, B, new, dev)
-        gathered = TD.gather_tokens(packed, n_total)          # the one collective (includes the D2H of the ids)
-        return outs, gathered
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(frames, k):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = model.launch_count()
-        phases, gen = [], 0
-        e0.record()
-        for _ in range(k):
-            outs, _ = step(frames)
-            phases.append(dict(model.last_timings))
-            gen += sum(len(o) for o in outs)
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            g = torch.tensor([gen], dtype=torch.int64, device=dev)
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            gen = int(g.item())
-        return ms, gen, phases, model.launch_count() - l0
+    wl = Workload(model, cfg, rank, world, dev, T, B, new)
 
     for _ in range(args.warmup):
-        step(dev_list)
+        wl.step(wl.dev_list)
     if args.profile:                       # one device-resident step for ncu launch lists; prints no bench line
-        sync_all()
+        wl.sync_all()
         torch.cuda.profiler.start()            # ncu --profile-from-start off: only this step is captured
-        step(dev_list)
-        sync_all()
+        wl.step(wl.dev_list)
+        wl.sync_all()
         torch.cuda.profiler.stop()
         if rank == 0:
             print(json.dumps({"profile_only": True, "phases_ms": model.last_timings}), flush=True)
@@ -246,9 +294,10 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, gen_dev, ph_dev, launches_eager = timed(dev_list, args.steps)
-    ms_e2e, gen_e2e, ph_e2e, _ = timed(host_list, args.steps)
+    ms_dev, gen_dev, ph_dev, launches_eager = wl.timed(wl.dev_list, args.steps)
+    ms_e2e, gen_e2e, ph_e2e, _ = wl.timed(wl.host_list, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    head = wl.summary(ms_dev, gen_dev, ph_dev, ms_e2e, gen_e2e, args.steps)
 
     # launches: eager calls are counted by the handle (teo_launch_count); a graph replay relaunches the kernels of one decode
     # step, counted on the eager step that preceded the capture (fallback: the upper bound 14 per layer + 6)
@@ -256,33 +305,58 @@ def run_gpu(args):
     replays = sum(p.get("graph_replays", 0) for p in ph_dev)
     gpu_launches = int(launches_eager + replays * per_step)
 
-    roof = decode_attention_roofline(model, cfg, B, S0 + new // 2, dev) if not args.tiny else None
+    # per-rank phase times (N > 1: the step time is the MAX over ranks, so the slowest rank's phases explain it)
+    per_rank = None
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, **head["phases_ms"]})
+
+    roof = decode_attention_roofline(model, cfg, B, wl.S0 + new // 2, dev) if not args.tiny else None
+
+    # the other BASELINE configs, measured briefly on the same replica (N = 1 only; the headline numbers above are final by now)
+    others = None
+    if world == 1 and not args.tiny and not args.no_other_configs:
+        others = {}
+        for ci, shape in CONFIGS.items():
+            if shape == (T, B, new):
+                continue
+            del wl
+            torch.cuda.empty_cache()
+            wl = Workload(model, cfg, rank, world, dev, *shape)
+            for _ in range(2):
+                wl.step(wl.dev_list)
+            r = wl.timed(wl.dev_list, 3)
+            e = wl.timed(wl.host_list, 3)
+            o = wl.summary(r[0], r[1], r[2], e[0], e[1], 3)
+            o["steps"], o["warmup"] = 3, 2
+            if ci == 4:
+                o["note"] = "configs[4] is bs=16 over 8 GPUs = this shape on every rank; run `--config 4` under torchrun for the 8-GPU number"
+            others[f"configs[{ci}]"] = o
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.tiny:
-        cb = cpu_reference_leg(*CPU_SAMPLE, 1, 0)
+        cb = cpu_reference_leg(*CPU_SAMPLE, 2, 1)
 
     if rank == 0:
-        k = args.steps
-        vit_fps = sum(p["frames"] for p in ph_dev) / (sum(p["vit_ms"] for p in ph_dev) / 1e3) * world
-        dec_tps = sum(p["batch"] * p["decode_steps"] for p in ph_dev) / (sum(p["decode_ms"] for p in ph_dev) / 1e3) * world
-        pre_tps = sum(p["prefill_tokens"] for p in ph_dev) / (sum(p["prefill_ms"] for p in ph_dev) / 1e3) * world
         pk = peaks()
         vit_flops = 155.3e9 + 10.74e9
         line = {
-            "metric": METRIC, "value": gen_dev / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": k, "warmup": args.warmup,
-            "ms_per_step": ms_dev / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"T={T} frames x bs={B} per GPU, context {S0}, {new} new tokens, greedy (BASELINE configs[2]/[3])",
-                       "global_batch": n_total, "seq_len": S0 + new, "parallelism": f"dp{world}",
+            "config": {"workload": head["workload"], "global_batch": head["global_batch"], "seq_len": None, "parallelism": f"dp{world}",
                        "l2": "working set (13.5 GB weights + KV pages) >> 126 MB L2; no flush needed", "weights": "random-init (hash) bf16"},
-            "vit_frames_per_s": vit_fps, "decode_tokens_per_s": dec_tps, "prefill_tokens_per_s": pre_tps,
-            "phases_ms": {kk: sum(p[kk] for p in ph_dev) / k for kk in ("vit_ms", "prefill_ms", "decode_ms")},
-            "vit_tensor_frac_of_measured_peak": (vit_fps / world) * vit_flops / (pk["bf16_tflops_sustained"] * 1e12),
-            "e2e": {"value": gen_e2e / (ms_e2e / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(frames_host.numel() + 4 * (3 * B * S0 + 3 * B + 1 + B * 64)),
-                    "d2h_bytes_per_step": int(B * new * 4), "ms_per_step": ms_e2e / k},
-            "gpu_launches": gpu_launches, "clocks": clocks, "peaks": pk,
+            "vit_frames_per_s": head["vit_frames_per_s"], "decode_tokens_per_s": head["decode_tokens_per_s"],
+            "prefill_tokens_per_s": head["prefill_tokens_per_s"], "phases_ms": head["phases_ms"],
+            "vit_tensor_frac_of_measured_peak": (head["vit_frames_per_s"] / world) * vit_flops / (pk["bf16_tflops_sustained"] * 1e12),
+            "vit_tensor_frac_of_burst_peak": (head["vit_frames_per_s"] / world) * vit_flops / (pk["bf16_tflops"] * 1e12),
+            "e2e": head["e2e"], "gpu_launches": gpu_launches, "clocks": clocks, "peaks": pk,
         }
+        line["config"]["seq_len"] = int(head["workload"].split("context ")[1].split(",")[0]) + new
+        if per_rank:
+            line["per_rank_phases_ms"] = per_rank
+        if others:
+            line["other_configs"] = others
         if roof:
             line["roofline"] = roof
         if cb:
@@ -344,6 +418,8 @@ def decode_attention_roofline(model, cfg, B, S, dev, iters=20):
     kernel = "decode_attn_mma_kernel" if (hd, ps) == (128, 64) and os.environ.get("TEO_DEC_ATTN") is None else "decode_attn_persist_kernel"
     return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get((B, S)) if kernel == "decode_attn_mma_kernel" else None,
+            "traffic_source": "static: dram__bytes_read+write of one `ncu --set full` capture at exactly this (bs, S), "
+                              "profiles/r01_decode_attn_mma.txt — not measured in this run",
             "peak_source": pk["source"] + " (burst copy)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms * 1e3,
             "how": f"bs={B}, S={S}, {iters} launches over 8 rotating layer pools, CUDA events"}
@@ -355,13 +431,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="teochat_b200", choices=["teochat_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="examples per GPU")
-    ap.add_argument("--frames", type=int, default=8)
-    ap.add_argument("--new-tokens", type=int, default=256)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[i] as the headline workload")
+    ap.add_argument("--batch", type=int, default=None, help="examples per GPU (default: the config's)")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--new-tokens", type=int, default=None)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short configs[1] / configs[4] measurements at N=1")
     ap.add_argument("--tiny", action="store_true", help="tiny config (plumbing check only; not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="run warm-up + exactly one step and exit (for ncu; not a bench number)")
     args = ap.parse_args()
+    T, B, new = CONFIGS[args.config]
+    args.frames = args.frames if args.frames is not None else T
+    args.batch = args.batch if args.batch is not None else B
+    args.new_tokens = args.new_tokens if args.new_tokens is not None else new
     if args.impl == "reference":
         run_reference(args)
     else:

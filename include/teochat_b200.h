@@ -48,6 +48,9 @@ int teo_create(int device_id, teo_handle** out);
 int teo_destroy(teo_handle* h);
 const char* teo_last_error(void);
 int teo_abi_version(void);
+/* digest of the sources this binary was compiled from (teochat_b200/build.py:source_digest); the Python loader refuses a
+ * library whose digest differs from the sources beside it */
+const char* teo_build_digest(void);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 unsigned long long teo_launch_count(const teo_handle* h);
 

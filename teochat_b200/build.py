@@ -2,6 +2,7 @@
 machinery: the product boundary is a plain C-ABI .so loaded through ctypes."""
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -22,12 +23,29 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+DIGEST_PATH = os.path.join(LIB_DIR, "libteochat_b200.digest")
+
+
+def source_digest() -> str:
+    """sha256 over everything the library is built from: csrc/* (names + bytes), the public header and the nvcc flags.
+    The digest is compiled INTO the library (teo_build_digest()) and lib.load() refuses a library whose digest differs from
+    the sources beside it — a stale .so cannot be picked up silently, wherever it was built."""
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(HERE, "..", "include", "teochat_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()[:16]
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(DIGEST_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "teochat_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(DIGEST_PATH) as f:
+        return f.read().strip() != source_digest()
 
 
 def build_variant(name: str, defines) -> str:
@@ -36,7 +54,8 @@ def build_variant(name: str, defines) -> str:
     vdir = os.path.join(LIB_DIR, "variants")
     os.makedirs(vdir, exist_ok=True)
     out = os.path.join(vdir, f"{name}.so")
-    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines], "-shared",
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines],
+           f'-DTEO_BUILD_DIGEST="{source_digest()}"', "-shared",
            *[os.path.join(CSRC, s) for s in SOURCES], "-o", out, "-cudart", "static"]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return out
@@ -46,11 +65,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    digest = source_digest()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, f'-DTEO_BUILD_DIGEST="{digest}"', "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -68,6 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(log))
     cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"]
     subprocess.check_call(cmd)
+    with open(DIGEST_PATH, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 

@@ -94,6 +94,10 @@ using namespace teo;
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" const char* teo_last_error(void) { return g_err; }
 extern "C" int teo_abi_version(void) { return 3; }
+#ifndef TEO_BUILD_DIGEST
+#define TEO_BUILD_DIGEST "unknown"
+#endif
+extern "C" const char* teo_build_digest(void) { return TEO_BUILD_DIGEST; }
 
 extern "C" int teo_create(int device_id, teo_handle** out) {
     TEO_CHECK_ARG(out != nullptr, "teo_create: null out");

@@ -57,6 +57,7 @@ _SIGS = {
     "teo_destroy": (i, [vp]),
     "teo_last_error": (C.c_char_p, []),
     "teo_abi_version": (i, []),
+    "teo_build_digest": (C.c_char_p, []),
     "teo_launch_count": (C.c_ulonglong, [vp]),
     "teo_init_normal_hash_bf16": (i, [vp, sz, u64, f, f, vp]),
     "teo_init_normal_hash_f32": (i, [vp, sz, u64, f, f, vp]),
@@ -118,6 +119,11 @@ def load() -> C.CDLL:
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)          # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args
+        if not os.environ.get("TEO_LIB_PATH"):       # the in-tree build must come from exactly the sources beside it
+            have, want = lib.teo_build_digest().decode(), _build.source_digest()
+            if have != want:
+                raise TeoError(f"{path} was built from other sources (digest {have}, sources {want}): "
+                               "run `python __graft_entry__.py build`")
         _LIB = lib
     return _LIB
 

@@ -29,7 +29,16 @@ def test_cpu_thread_choice_is_bounded():
         assert bench.pick_cpu_threads() == 3
     finally:
         del os.environ["TEO_CPU_THREADS"]
-    assert 1 <= bench.pick_cpu_threads() <= max(n, 4)
+    assert bench.pick_cpu_threads() == n                # fixed policy: every usable CPU
+
+
+def test_configs_table_matches_baseline_json():
+    with open(os.path.join(ROOT, "BASELINE.json")) as f:
+        cfgs = json.load(f)["configs"]
+    assert "bs=64" in cfgs[1] and "128 output tokens" in cfgs[1] and bench.CONFIGS[1] == (1, 64, 128)
+    assert "T=8" in cfgs[2] and "bs=32" in cfgs[2] and "256 output tokens" in cfgs[2] and bench.CONFIGS[2] == (8, 32, 256)
+    assert "T=16" in cfgs[4] and "bs=16" in cfgs[4] and "512 output tokens" in cfgs[4] and bench.CONFIGS[4] == (16, 16 // 8, 512)
+    assert bench.CPU_SAMPLE == (2, 16) and "2-frame" in cfgs[0] and "16 tokens" in cfgs[0]
 
 
 def test_reference_arm_json_line_on_tiny_config(monkeypatch, capsys):
@@ -42,6 +51,8 @@ def test_reference_arm_json_line_on_tiny_config(monkeypatch, capsys):
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 2 and cb["value"] == line["value"] and "new tokens" in cb["sample"]
+    assert line["same_config"] is False and line["kind"] == "port" and "configs[0]" in cb["sample"] and "configs[0]" in line["config"]["sample"]
+    assert "configs[2]" in line["config"]["workload"]            # the GPU arm's workload is named, the CPU sample beside it
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
