@@ -183,6 +183,10 @@ int teo_sample_step(const void* logits, int vocab, float temperature, int top_k,
 /* select how teo_llama_decode_step picks the next token for this handle: temperature <= 0 → greedy */
 int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed);
 
+/* the decode step reads the sampling seed from device memory (u64 [1]) instead of the value given to teo_set_sampling, so
+ * that one captured CUDA graph of the step serves every seed; NULL switches back to the host value */
+int teo_set_sampling_seed_device(teo_handle* h, const void* seed_u64_device);
+
 /* programmatic dependent launch between the kernels of teo_llama_decode_step (default on): each kernel's launch,
  * prologue and — for the GEMMs — weight prefetch overlap the tail of its predecessor.  Results are identical. */
 int teo_set_pdl(teo_handle* h, int enabled);

@@ -1,8 +1,10 @@
 """HF-format checkpoint loading for the hot path: merged checkpoints, LoRA
 checkpoints (adapter + ``non_lora_trainables.bin``) over a base model, and a separate image-tower
 checkpoint — the branches of ``videollava/model/builder.py:33-155`` that matter for TEOChat
-(``scripts/merge_lora_weights.py:10-31`` for the merge semantics, ``modeling_image.py:775-793`` for the tower's
-LoRA).  Everything here is host-side tensor plumbing; the result is an HF-named state dict that
+(``scripts/merge_lora_weights.py:10-31`` for the merge semantics).  The image tower's encoder is PEFT-wrapped by the
+reference itself (``modeling_image.py:773-792``, default ``lora_r=2, lora_alpha=16``): its keys look like
+``…encoder.base_model.model.layers.N.self_attn.q_proj.base_layer.weight`` + ``…lora_A/B.default.weight`` and the adapter
+runs UNMERGED at scaling 8 — here it is merged into the tower weights at load (``tower_lora_scaling``).  Everything here is host-side tensor plumbing; the result is an HF-named state dict that
 ``TeoWeights.from_state_dict`` lays out for the kernels.
 
 No checkpoint, tokenizer or network exists in the build container, so this module is exercised on synthetic
@@ -89,6 +91,9 @@ def _canon(name: str) -> Optional[str]:
     if name.startswith("model.model."):
         name = name[len("model."):]
     name = name.replace(".base_layer.", ".")                       # PEFT-wrapped Linear
+    # the image tower's ENCODER is itself a PeftModel (LanguageBindImage.convert_to_lora, modeling_image.py:773-792:
+    # vision_model.encoder = get_peft_model(encoder, …)), so its keys carry an inner wrapper prefix
+    name = name.replace(".encoder.base_model.model.", ".encoder.")
     if name.startswith("vision_model."):                          # stand-alone LanguageBind_Image / CLIPVisionModel checkpoint
         name = VIT + name[len("vision_model."):]
     if name.startswith("model.image_tower.image_tower.vision_model."):
@@ -121,6 +126,23 @@ def merge_lora_(sd: Dict[str, torch.Tensor], adapter: Dict[str, torch.Tensor], s
     return n
 
 
+def tower_lora_scaling(*dirs: Optional[str]) -> float:
+    """lora_alpha / lora_r of the image tower's built-in adapter: the first config.json among `dirs` that names them
+    (top level or under vision_config), else the class defaults of configuration_image.py:200-201 (r=2, alpha=16)."""
+    for d in dirs:
+        if not d or not os.path.isfile(os.path.join(d, "config.json")):
+            continue
+        with open(os.path.join(d, "config.json")) as f:
+            c = json.load(f)
+        for scope in (c.get("vision_config") or {}, c):
+            if "lora_r" in scope:
+                r = float(scope["lora_r"])
+                if r == 0:
+                    return 0.0
+                return float(scope.get("lora_alpha", 16)) / r
+    return 16.0 / 2.0
+
+
 def load_state_dict(model_path: str, model_base: Optional[str] = None, tower_path: Optional[str] = None) -> Dict[str, torch.Tensor]:
     """HF-named state dict of the hot path from
        - a merged checkpoint directory (model_base None), or
@@ -128,16 +150,26 @@ def load_state_dict(model_path: str, model_base: Optional[str] = None, tower_pat
        plus, if the tower weights are not inside, a separate tower checkpoint directory."""
     base_dir = model_base or model_path
     sd: Dict[str, torch.Tensor] = {}
+    tower_lora: Dict[str, torch.Tensor] = {}     # the tower's own (unmerged) adapter: it runs at lora_alpha/lora_r in the reference
     for shard in iter_shards(base_dir):
         for k, t in shard.items():
-            if _lora_key(_canon(k)) is None:
-                sd[_canon(k)] = t
+            ck = _canon(k)
+            if _lora_key(ck) is None:
+                sd[ck] = t
+            elif ck.startswith(VIT):
+                tower_lora[ck] = t
+    tower_src = base_dir
     if tower_path and not any(k.startswith(VIT) for k in sd):
+        tower_src = tower_path
         for shard in iter_shards(tower_path):
             for k, t in shard.items():
                 ck = _canon(k)
-                if ck.startswith(VIT) and _lora_key(ck) is None:
+                if not ck.startswith(VIT):
+                    continue
+                if _lora_key(ck) is None:
                     sd[ck] = t
+                else:
+                    tower_lora[ck] = t
     if model_base is not None:
         nl = os.path.join(model_path, "non_lora_trainables.bin")          # projector etc. trained without LoRA (builder.py:52-66)
         if os.path.exists(nl):
@@ -155,6 +187,15 @@ def load_state_dict(model_path: str, model_base: Optional[str] = None, tower_pat
         else:
             ad = torch.load(adapters[0], map_location="cpu", weights_only=True)
         merge_lora_(sd, ad, scaling)
+        # a LoRA checkpoint may carry re-trained tower adapters among its non-LoRA trainables: they win over the tower's own
+        for k in [k for k in sd if _lora_key(k) is not None]:
+            t = sd.pop(k)
+            if k.startswith(VIT):
+                tower_lora[k] = t
+    if tower_lora:
+        s = tower_lora_scaling(tower_src, model_path, model_base)
+        if s != 0.0:
+            merge_lora_(sd, tower_lora, s)
     return sd
 
 

@@ -43,29 +43,47 @@ class Conversation:
                             sep_style=self.sep_style, sep=self.sep, sep2=self.sep2,
                             version=self.version)
 
+    def _messages(self):
+        """conversation.py:31-42: when the first message carries an image (a (text, image, mode) tuple, the demo's form),
+        its ``<image>`` tag is moved to the front (``<image>\n`` + text), or — for ``mmtag`` versions — sent as a separate
+        ``<Image><image></Image>`` / ``Received.`` exchange."""
+        messages = self.messages
+        if len(messages) > 0 and type(messages[0][1]) is tuple:
+            messages = [list(m) for m in self.messages]
+            init_role, init_msg = messages[0]
+            init_msg = init_msg[0].replace("<image>", "").strip()
+            if "mmtag" in self.version:
+                messages[0] = [init_role, init_msg]
+                messages.insert(0, [self.roles[0], "<Image><image></Image>"])
+                messages.insert(1, [self.roles[1], "Received."])
+            else:
+                messages[0] = [init_role, "<image>\n" + init_msg]
+        return messages
+
     def get_prompt(self) -> str:
         style = self.sep_style
+        messages = self._messages()
         if style == SeparatorStyle.SINGLE:
             out = self.system + self.sep
-            for role, message in self.messages:
+            for role, message in messages:
                 out += (role + ": " + _text(message) + self.sep) if message else (role + ":")
             return out
         if style == SeparatorStyle.TWO:
             seps = (self.sep, self.sep2)
             out = self.system + seps[0]
-            for i, (role, message) in enumerate(self.messages):
+            for i, (role, message) in enumerate(messages):
                 out += (role + ": " + _text(message) + seps[i % 2]) if message else (role + ":")
             return out
         if style == SeparatorStyle.PLAIN:
             seps = (self.sep, self.sep2)
             out = self.system
-            for i, (_, message) in enumerate(self.messages):
+            for i, (_, message) in enumerate(messages):
                 if message:
                     out += _text(message) + seps[i % 2]
             return out
         if style == SeparatorStyle.LLAMA_2:
             out = ""
-            for i, (role, message) in enumerate(self.messages):
+            for i, (role, message) in enumerate(messages):
                 if i == 0:
                     assert message, "first message should not be none"
                     assert role == self.roles[0], "first message should come from user"

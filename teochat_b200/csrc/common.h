@@ -107,6 +107,7 @@ struct teo_handle {
     float temperature = 0.f;           // > 0 → teo_llama_decode_step samples (teo_set_sampling)
     int top_k = 50;
     unsigned long long sample_seed = 0;
+    const unsigned long long* sample_seed_ptr = nullptr;   // device-resident seed (teo_set_sampling_seed_device); wins over sample_seed
     bool pdl = true;                   // programmatic dependent launch inside teo_llama_decode_step (teo_set_pdl)
     std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
 };
@@ -149,6 +150,13 @@ __host__ __device__ inline int partial_count(const PartialInfo& pi, int col) {
     if (last > pi.grid - 1) last = pi.grid - 1;
     return last - first + 1;
 }
+
+// next-token kernels (kernels_misc.cu); step_ptr / seed_ptr != nullptr: column / seed read from device memory (graph replay)
+int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
+                       int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
+int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
+                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream,
+                       const unsigned long long* seed_ptr = nullptr);
 
 // Small-M (decode) GEMM that stops at the fp32 partials; the consumer kernel reduces them (fixed slot order).
 int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,

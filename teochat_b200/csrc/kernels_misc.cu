@@ -618,8 +618,9 @@ __device__ __forceinline__ uint32_t float_order_key(float f) {          // monot
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int vocab, float inv_temp, int top_k,
-                                                          unsigned long long seed, uint8_t* finished, int* tokens, int max_new,
-                                                          int step_host, const int* step_ptr, int* next_ids, int* seq_lens, int eos_id) {
+                                                          unsigned long long seed, const unsigned long long* seed_ptr, uint8_t* finished,
+                                                          int* tokens, int max_new, int step_host, const int* step_ptr, int* next_ids,
+                                                          int* seq_lens, int eos_id) {
     __shared__ uint32_t hist[256];
     __shared__ float redf[8];
     __shared__ uint32_t sh_prefix, sh_remaining;
@@ -678,6 +679,7 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
         float total = 0.f;
         for (int i = 0; i < 256; ++i) total += sh_scan[i];
         const int step = step_ptr ? *step_ptr : step_host;
+        if (seed_ptr) seed = *seed_ptr;           // device-resident seed: a captured decode graph is reusable across seeds
         const uint64_t r = splitmix64(seed + (static_cast<uint64_t>(step) * 0x100000001B3ULL + static_cast<uint64_t>(seq) + 1ULL) * 0x9E3779B97F4A7C15ULL);
         const float u = static_cast<float>(r >> 40) * (1.0f / 16777216.0f);      // [0,1)
         float target = u * total, acc = 0.f;
@@ -883,11 +885,12 @@ int launch_reduce_rope_kv_write(const PartialInfo& pi, void* qkv, const int* pos
     return TEO_OK;
 }
 int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
-                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream) {
+                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream,
+                       const unsigned long long* seed_ptr) {
     TEO_CHECK_ARG(logits && finished && tokens && next_ids, "sample_step: null pointer");
     TEO_CHECK_ARG(n_seqs > 0 && vocab > 0 && max_new > 0 && temperature > 0.f, "sample_step: bad sizes / temperature");
     if (top_k <= 0 || top_k > vocab) top_k = vocab;
-    TEO_CUDA(launch_k(sample_step_kernel, dim3(n_seqs), dim3(256), 0, stream, logits, vocab, 1.0f / temperature, top_k, seed, finished, tokens, max_new,
+    TEO_CUDA(launch_k(sample_step_kernel, dim3(n_seqs), dim3(256), 0, stream, logits, vocab, 1.0f / temperature, top_k, seed, seed_ptr, finished, tokens, max_new,
                       step_host, static_cast<const int*>(step_ptr), next_ids, seq_lens, eos_id));
     TEO_LAUNCH_CHECK("sample_step_kernel");
     if (step_ptr) {

@@ -52,11 +52,6 @@ int launch_decode_attention(teo_handle* h, const bf16* q, int ldq, const bf16* k
 int launch_rope_kv_write(void* qkv, const int* positions, const int* seq_ids, void* kv_pages, const int* block_table, int max_pages,
                          int tokens, int n_heads, int head_dim, int page_size, const float* rope_cos, const float* rope_sin,
                          cudaStream_t stream);
-int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
-                       int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
-
-int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
-                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
 int launch_reduce_residual_rmsnorm(const PartialInfo& pi, bf16* x, const bf16* w, bf16* y, int rows, int d, float eps, cudaStream_t stream);
 int launch_reduce_swiglu(const PartialInfo& pi, bf16* act, int rows, int inter, int interleaved, cudaStream_t stream);
 int launch_swiglu(const void* gate_up, void* out, int rows, int inter, int interleaved, cudaStream_t stream);
@@ -128,6 +123,11 @@ extern "C" int teo_set_sampling(teo_handle* h, float temperature, int top_k, uin
     h->temperature = temperature;
     h->top_k = top_k;
     h->sample_seed = seed;
+    return TEO_OK;
+}
+extern "C" int teo_set_sampling_seed_device(teo_handle* h, const void* seed_u64_device) {
+    TEO_CHECK_ARG(h != nullptr, "teo_set_sampling_seed_device: null handle");
+    h->sample_seed_ptr = static_cast<const unsigned long long*>(seed_u64_device);
     return TEO_OK;
 }
 extern "C" int teo_set_pdl(teo_handle* h, int enabled) {
@@ -504,7 +504,7 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     if (h->temperature > 0.f)
         TEO_TRY(launch_sample_step(static_cast<const float*>(logits), m->vocab, h->temperature, h->top_k, h->sample_seed,
                                    static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new, 0, static_cast<int*>(step_ptr),
-                                   static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream));
+                                   static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream, h->sample_seed_ptr));
     else
         TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
                                    max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,

@@ -26,10 +26,6 @@ int x_attention(bool paged, const float* qkv, int ld, float* out, int ldo, const
                 int max_keys, float scale, cudaStream_t s);
 int x_fill_seq_ids(int* seq_ids, int rows, int len, cudaStream_t s);
 int x_patchify(bool u8, const void* in, void* patches3, int n_frames, int image, int patch, int kpad, cudaStream_t stream);
-int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* tokens, int max_new, int step_host, int* step_ptr,
-                       int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
-int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
-                       int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream);
 
 // C f32 [M,N] = A3 (three bf16 planes of an fp32 [M,K]) · W[N,K]^T + bias (+ fp32 residual, may alias C)
 static int gemm_x(teo_handle* h, const bf16* a3, const void* W, float* C, int M, int N, int K, const void* bias, const float* residual,
@@ -262,7 +258,7 @@ int llama_decode_step_exact(teo_handle* h, const teo_llama_model* m, void* next_
     if (h->temperature > 0.f)
         TEO_TRY(launch_sample_step(static_cast<const float*>(logits), m->vocab, h->temperature, h->top_k, h->sample_seed,
                                    static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new, 0, static_cast<int*>(step_ptr),
-                                   static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream));
+                                   static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream, h->sample_seed_ptr));
     else
         TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
                                    max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,

@@ -263,7 +263,7 @@ class TeoModel:
             raise ValueError("max_new_tokens must be >= 1")
         eos = l.eos_token_id if eos_token_id is None else eos_token_id
         sampling = temperature is not None and temperature > 0
-        L.check(self.lib.teo_set_sampling(self._h, float(temperature) if sampling else 0.0, int(top_k), C.c_uint64(seed & (2 ** 64 - 1))),
+        L.check(self.lib.teo_set_sampling(self._h, float(temperature) if sampling else 0.0, int(top_k), C.c_uint64(seed & (2 ** 63 - 1))),
                 "teo_set_sampling")
         imgs = frames_u8 if frames_u8 is not None else pixel_values
         if imgs is None or len(imgs) != B:
@@ -325,16 +325,20 @@ class TeoModel:
         # ---- per-shape decode state with stable addresses, so the captured decode graph is reused across calls
         dwb = self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len)
         dws = self._ws("decode", dwb)
-        key = (B, max_new_tokens, max_pages, total_len, eos, sampling, float(temperature or 0.0), int(top_k), int(seed), self.use_pdl)
+        # the seed is NOT part of the key: the captured step reads it from device memory (st.seed_dev)
+        key = (B, max_new_tokens, max_pages, total_len, eos, sampling, float(temperature or 0.0) if sampling else 0.0,
+               int(top_k) if sampling else 0, self.use_pdl)
         st = self._decode_states.get(key)
-        if st is None or st.pool_ptr != self._kv_pool.data_ptr() or st.dws_ptr != dws.data_ptr():
+        # a captured graph bakes in the per-layer page-pool pointers (pool base + layer · n_pages · page bytes) and the workspace
+        pool_id = (self._kv_pool.data_ptr(), int(self._kv_pool.shape[1]))
+        if st is None or st.pool_id != pool_id or st.dws_ptr != dws.data_ptr():
             with torch.inference_mode(False):     # cached across calls: must stay ordinary tensors (callers may use inference_mode)
                 st = SimpleNamespace(
                     d_len=torch.empty(B, dtype=torch.int32, device=dev), d_bt=torch.empty(B * max_pages, dtype=torch.int32, device=dev),
                     logits=torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev),
                     finished=torch.empty(B, dtype=torch.uint8, device=dev), tokens=torch.empty(B, max_new_tokens, dtype=torch.int32, device=dev),
                     next_ids=torch.empty(B, dtype=torch.int32, device=dev), step_ptr=torch.empty(1, dtype=torch.int32, device=dev),
-                    graph=None, pool_ptr=self._kv_pool.data_ptr(), dws_ptr=dws.data_ptr())
+                    seed_dev=torch.empty(1, dtype=torch.int64, device=dev), graph=None, pool_id=pool_id, dws_ptr=dws.data_ptr())
             if len(self._decode_states) >= 4:
                 self._decode_states.pop(next(iter(self._decode_states)))
             self._decode_states[key] = st
@@ -345,6 +349,8 @@ class TeoModel:
         finished.zero_()
         tokens.fill_(-1)
         step_ptr.fill_(1)
+        st.seed_dev.fill_(int(seed) & (2 ** 63 - 1))
+        L.check(self.lib.teo_set_sampling_seed_device(self._h, st.seed_dev.data_ptr()), "teo_set_sampling_seed_device")
         x = self._ws("x", T * h * proj.element_size())
         splice = self.lib.teo_splice_embed_f32 if self.exact else self.lib.teo_splice_embed
         L.check(splice(self.w.t["llama.embed"].data_ptr(), proj.data_ptr(), d_src.data_ptr(), x.data_ptr(), T, h, stream), "teo_splice_embed")
@@ -354,7 +360,7 @@ class TeoModel:
                                            d_sid.data_ptr(), d_last.data_ptr(), B, max_len, d_bt.data_ptr(), max_pages,
                                            logits.data_ptr(), pws.data_ptr(), pws.numel(), stream), "teo_llama_prefill")
         if sampling:
-            L.check(self.lib.teo_sample_step(logits.data_ptr(), l.vocab_size, float(temperature), int(top_k), C.c_uint64(seed & (2 ** 64 - 1)),
+            L.check(self.lib.teo_sample_step(logits.data_ptr(), l.vocab_size, float(temperature), int(top_k), C.c_uint64(seed & (2 ** 63 - 1)),
                                              finished.data_ptr(), tokens.data_ptr(), max_new_tokens, 0, next_ids.data_ptr(), B, eos, stream),
                     "teo_sample_step")
         else:
@@ -433,10 +439,10 @@ class TeoModel:
             raise ValueError("generate expects input_ids of shape [1, L]; use generate_batch for batches")
         sample_t = float(temperature) if (do_sample and temperature and temperature > 0) else 0.0
         eos = self.cfg.llama.eos_token_id
-        if stopping_criteria:
-            for sc in stopping_criteria:
-                if hasattr(sc, "is_eos_only") and not sc.is_eos_only(eos):
-                    raise NotImplementedError("only the eval path's [\"</s>\"] stopping rule runs on the device")
+        # The eval path's ["</s>"] rule runs on the device (last id == eos).  Any other criterion (multi-token stop strings of
+        # the llava_llama_2 / plain templates, user criteria) is evaluated on the host over the generated prefix afterwards —
+        # same result as HF's per-token check, because step n of the decode does not depend on later steps.
+        host_criteria = [sc for sc in (stopping_criteria or []) if not (hasattr(sc, "is_eos_only") and sc.is_eos_only(eos))]
         if isinstance(images, (list, tuple)):
             px = torch.stack([im.to(torch.float32) for im in images]) if len(images) else None
         else:
@@ -449,4 +455,10 @@ class TeoModel:
         out = self.generate_batch([ids], pixel_values=[px], max_new_tokens=max_new_tokens, temperature=sample_t,
                                   top_k=int(kwargs.get("top_k", 50) or 0), seed=int(kwargs.get("seed", 0)))[0]
         new = torch.tensor(out, dtype=input_ids.dtype, device=input_ids.device)[None]
-        return torch.cat([input_ids, new], dim=1)
+        full = torch.cat([input_ids, new], dim=1)
+        if host_criteria:
+            L0 = input_ids.shape[1]
+            for n in range(1, len(out) + 1):
+                if any(bool(sc(full[:, :L0 + n], None)) for sc in host_criteria):       # HF stops when ANY criterion fires
+                    return full[:, :L0 + n]
+        return full

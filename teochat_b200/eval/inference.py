@@ -73,18 +73,32 @@ def run_inference_batch(model, processor, tokenizer, inps: Sequence[str], image_
                         max_new_tokens=256, seed: int = 0) -> List[str]:
     """Batched greedy form of run_inference_single: one ViT pass over all frames, one ragged
     prefill, one graph-replayed decode loop.  Result i equals run_inference_single on example i."""
-    ids_list, frames = [], []
+    ids_list, frames, stops = [], [], []
     on_device = hasattr(processor, "preprocess_device") and getattr(model, "device", torch.device("cpu")).type == "cuda"
     for n, (inp, paths) in enumerate(zip(inps, image_paths_list)):
         ts = timestamps_list[n] if timestamps_list is not None else ()
-        prompt, paths, _ = build_prompt(inp, paths, conv_mode, ts, prompt_strategy, chronological_prefix)
+        prompt, paths, stop_str = build_prompt(inp, paths, conv_mode, ts, prompt_strategy, chronological_prefix)
         ids_list.append(tokenizer_image_token(prompt, tokenizer, IMAGE_TOKEN_INDEX))
+        stops.append(stop_str)
         if on_device:        # raw uint8 over PCIe, ToTensor/Resize/CenterCrop/Normalize in CUDA (teo_resize_crop_normalize_u8)
             frames.append(processor.preprocess_device(list(paths), model.device))
         else:
             frames.append(torch.cat([processor.preprocess(p, return_tensors="pt")["pixel_values"] for p in paths]))
     outs = model.generate_batch(ids_list, pixel_values=frames, max_new_tokens=max_new_tokens,
                                 temperature=temperature or 0.0, seed=seed)
+    eos = model.cfg.llama.eos_token_id if hasattr(model, "cfg") else None
+    for n, (ids, out) in enumerate(zip(ids_list, outs)):
+        # templates whose stop string is not "</s>" (llava_llama_2: "<s>", plain: "\n"): the same KeywordsStoppingCriteria the
+        # single-example path builds, evaluated on the host over the generated prefix
+        prompt_ids = torch.tensor([ids])
+        sc = KeywordsStoppingCriteria([stops[n]], tokenizer, prompt_ids)
+        if eos is not None and sc.is_eos_only(eos):
+            continue
+        full = torch.cat([prompt_ids, torch.tensor([out], dtype=prompt_ids.dtype)], dim=1)
+        for k in range(1, len(out) + 1):
+            if sc(full[:, :len(ids) + k], None):
+                outs[n] = out[:k]
+                break
     return [tokenizer.decode(o).replace("</s>", "").strip() for o in outs]
 
 

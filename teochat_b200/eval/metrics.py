@@ -149,9 +149,10 @@ class PixelConfusion:
                     "f1": f1, "IoU": tp / (fp + fn + tp)}
 
 
-def evaluate_masks(results: Iterable[dict], height: int = 256, width: int = 256) -> Dict[str, float]:
-    """Pixel metrics of predicted boxes against the ground-truth polygons (detection.py:161-216).  A sample whose
-    ground truth / response has no ``[`` contributes an empty mask on that side."""
+def evaluate_masks(results: Iterable[dict], dataset=None, height: int = 256, width: int = 256) -> Dict[str, float]:
+    """Pixel metrics of predicted boxes against the ground-truth polygons (detection.py:161-216, same positional
+    signature: ``evaluate_masks(results, dataset, height=256, width=256)`` — ``dataset`` only labels the reference's
+    progress bar).  A sample whose ground truth / response has no ``[`` contributes an empty mask on that side."""
     conf = PixelConfusion(2)
     for r in results:
         gt = rasterise(parse_wkt_exteriors(r["polygon"]), (height, width)) if "[" in r["ground_truth"] \
@@ -175,6 +176,8 @@ def region_class_f1(outputs: Iterable[dict], classes: Sequence[str], skip_classe
             continue
         area = int((rasterise(parse_wkt_exteriors(out["polygon"]), (height, width)) > 0).sum())
         if pred in classes:
+            if truth not in classes:        # detection.py:246: classes.index(ground_truth_class) raises here
+                raise ValueError(f"{truth!r} is not in list")
             # the region is painted with one predicted and one true label: all-or-nothing per example
             tp = area if pred == truth else 0
             stats[pred]["tp"] += tp

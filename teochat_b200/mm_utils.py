@@ -98,8 +98,7 @@ class KeywordsStoppingCriteria:
             kid = kid.to(output_ids.device)
             if output_ids.shape[1] >= kid.shape[0] and bool((output_ids[0, -kid.shape[0]:] == kid).all()):
                 return True
-        if offset <= 0:
-            return False
+        # offset == 0 slices `[:, -0:]` = the WHOLE sequence, prompt included — the reference's behaviour (mm_utils.py:94), kept
         text = self.tokenizer.batch_decode(output_ids[:, -offset:], skip_special_tokens=True)[0]
         return any(k in text for k in self.keywords)
 

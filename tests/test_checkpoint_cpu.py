@@ -84,6 +84,66 @@ def test_lora_over_base_with_separate_tower(tmp_path, tiny_sd):
         CK.merge_lora_({}, ad, 1.0)
 
 
+def test_peft_wrapped_tower_is_merged(tmp_path, tiny_sd):
+    """The reference PEFT-wraps the tower's encoder (modeling_image.py:773-792): q/k/v/out_proj appear as
+    …encoder.base_model.model.layers.N.self_attn.X.base_layer.weight + lora_A/B.default.weight, and the adapter runs unmerged at
+    lora_alpha / lora_r (class defaults 16 / 2).  The loader must map the names and merge W += 8·B·A — both for a tower stored
+    inside the merged LLaVA checkpoint and for a separate LanguageBind_Image directory with its own config."""
+    cfg, sd = tiny_sd
+    g = torch.Generator().manual_seed(1)
+    r = 2
+    want = {k: v.clone() for k, v in sd.items()}
+
+    def wrap(prefix_in, prefix_out, scaling):
+        out = {}
+        for k, v in sd.items():
+            if not k.startswith(CK.VIT):
+                continue
+            rest = k[len(CK.VIT):]
+            if rest.startswith("encoder.layers."):
+                rest = "encoder.base_model.model." + rest[len("encoder."):]
+                parts = rest.split(".")
+                if parts[-2] in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                    mod = ".".join(parts[:-1])
+                    out[prefix_out + mod + ".base_layer." + parts[-1]] = v.contiguous()
+                    if parts[-1] == "weight":
+                        A, B = torch.randn(r, v.shape[1], generator=g) * 0.05, torch.randn(v.shape[0], r, generator=g) * 0.05
+                        out[prefix_out + mod + ".lora_A.default.weight"], out[prefix_out + mod + ".lora_B.default.weight"] = A, B
+                        want[k] = sd[k].float() + scaling * (B @ A)
+                    continue
+            out[prefix_out + rest] = v.contiguous()
+        return out
+
+    # (a) tower inside the LLaVA checkpoint, no lora fields in the config -> class defaults 16/2
+    d = str(tmp_path / "teochat-merged-peft-tower")
+    os.makedirs(d)
+    _write_config(d, cfg)
+    tw = wrap(CK.VIT, CK.VIT, 8.0)
+    rest = {k: v.contiguous() for k, v in sd.items() if not k.startswith(CK.VIT)}
+    save_file({**rest, **tw}, os.path.join(d, "model.safetensors"))
+    got = CK.load_state_dict(d)
+    assert set(got) == set(sd)
+    for k in sd:
+        assert torch.allclose(got[k].float(), want[k].float(), atol=1e-6, rtol=0), k
+    TeoWeights.from_state_dict(got, cfg, "cpu")
+
+    # (b) separate tower directory whose config names lora_r / lora_alpha
+    want = {k: v.clone() for k, v in sd.items()}
+    base, tower = str(tmp_path / "llava-notower"), str(tmp_path / "LanguageBind_Image_peft")
+    os.makedirs(base)
+    os.makedirs(tower)
+    _write_config(base, cfg)
+    save_file(rest, os.path.join(base, "model.safetensors"))
+    with open(os.path.join(tower, "config.json"), "w") as f:
+        json.dump({"vision_config": {"lora_r": r, "lora_alpha": 4}}, f)
+    save_file(wrap(CK.VIT, "vision_model.", 2.0), os.path.join(tower, "model.safetensors"))
+    got = CK.load_state_dict(base, tower_path=tower)
+    assert set(got) == set(sd)
+    for k in sd:
+        assert torch.allclose(got[k].float(), want[k].float(), atol=1e-6, rtol=0), k
+    assert CK.tower_lora_scaling(tower) == 2.0 and CK.tower_lora_scaling(None, base) == 8.0
+
+
 def test_rejects_unsupported(tmp_path, tiny_sd):
     cfg, _ = tiny_sd
     d = str(tmp_path / "teochat-gqa")

@@ -25,6 +25,12 @@ def test_pixel_metrics_match_reference():
     got = M.evaluate_masks(GOLD["cases"]["xbd_loc"])
     for k, v in GOLD["evaluate_masks_xbd_loc"].items():
         assert got[k] == pytest.approx(v, rel=1e-12), k
+    # the reference's positional call evaluate_masks(results, dataset) (detection.py:161) must bind the same way here
+    assert M.evaluate_masks(GOLD["cases"]["xbd_loc"], "xbd_loc") == got
+    # a ground-truth class outside `classes` raises like classes.index() does in the reference (detection.py:246)
+    poly = "POLYGON ((0 0, 0 10, 10 10, 10 0, 0 0))"
+    with pytest.raises(ValueError):
+        M.region_class_f1([{"response": "destroyed", "ground_truth": "flattened", "polygon": poly}], M.DAMAGE_CLASSES)
 
 
 def test_wkt_parser():

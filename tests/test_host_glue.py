@@ -73,6 +73,29 @@ def test_keywords_stopping_criteria():
     assert not sc2.is_eos_only(tok.eos_token_id)
     gen = torch.tensor([tok("go stop").input_ids[1:]])
     assert sc2(torch.cat([prompt, gen], 1), None)
+    # zero new tokens: the reference slices output_ids[:, -0:] = everything, so a keyword inside the PROMPT fires (mm_utils.py:94)
+    p2 = torch.tensor([tok("please stop").input_ids])
+    assert KeywordsStoppingCriteria(["stop"], tok, p2)(p2, None)
+
+
+def test_conversation_tuple_message_and_other_templates():
+    """conversation.py:31-42: a first message that carries an image (tuple) gets its <image> tag moved to the front; the
+    llava_llama_2 and plain templates build the reference's strings and stop strings."""
+    from teochat_b200.conversation import conv_templates
+    from teochat_b200.eval.inference import build_prompt
+    c = conv_templates["v1"].copy()
+    c.append_message(c.roles[0], ("What is <image> this?", object(), "Pad"))
+    c.append_message(c.roles[1], None)
+    assert c.get_prompt() == c.system + " USER: <image>\nWhat is  this? ASSISTANT:"
+    assert c.messages[0][1][0] == "What is <image> this?"              # the stored conversation is untouched
+    l2 = conv_templates["llava_llama_2"].copy()
+    l2.append_message(l2.roles[0], "hi <image>")
+    l2.append_message(l2.roles[1], None)
+    assert l2.get_prompt() == f"[INST] <<SYS>>\n{l2.system}\n<</SYS>>\n\nhi <image> [/INST]"
+    _, _, stop = build_prompt("x <video>", ["a"], conv_mode="llava_llama_2")
+    assert stop == "<s>"
+    prompt, _, stop = build_prompt("x <video>", ["a"], conv_mode="plain")
+    assert stop == "\n" and prompt == "x Image 1: <image>\n"
 
 
 def test_misc_helpers():
