@@ -134,6 +134,21 @@ int teo_flash_attention_tc(teo_handle* h, const void* q, int ldq, const void* k,
 
 /* KV pages: one pool per layer, bf16 [n_pages][2 (K,V)][n_heads][page_size][head_dim]
  * (replaces HF's torch.cat KV growth).  block_table int32 [n_seqs, max_pages]. */
+/* Page management (host side; the pools are caller-owned device memory, one per layer, the same page id indexes every
+ * layer's pool).  teo_kv_pool_bytes: bytes of ONE layer's pool.  teo_kv_plan: pages each sequence needs to hold its
+ * prompt plus max_new_tokens, their maximum (= block-table row length) and sum (= pool size for a fresh batch).
+ * teo_kv_create/alloc/free/destroy: a free-list allocator over n_pages page ids — teo_kv_alloc hands a sequence
+ * ceil(n_tokens/page_size) ids (lowest free first) and returns their count, teo_kv_free returns the pages of a retired
+ * sequence to the pool (continuous batching / sequence retirement). */
+typedef struct teo_kv_allocator teo_kv_allocator;
+size_t teo_kv_pool_bytes(int n_pages, int n_heads, int page_size, int head_dim, int exact);
+int teo_kv_plan(const int* host_seq_lens, int n_seqs, int max_new_tokens, int page_size, int* host_pages_per_seq,
+                int* max_pages_out, int* total_pages_out);
+int teo_kv_create(int n_pages, teo_kv_allocator** out);
+int teo_kv_destroy(teo_kv_allocator* a);
+int teo_kv_available(const teo_kv_allocator* a);
+int teo_kv_alloc(teo_kv_allocator* a, int n_tokens, int page_size, int* host_pages_out, int max_pages);
+int teo_kv_free(teo_kv_allocator* a, const int* host_pages, int n_pages);
 /* RoPE (rotate-half, HF LlamaRotaryEmbedding) on q and k in place inside a fused qkv buffer
  * bf16 [tokens, 3*n_heads*head_dim], then scatter k,v rows into the pages.
  * positions int32 [tokens]; seq_ids int32 [tokens] (row of block_table; NULL → token index).

@@ -81,6 +81,7 @@ class TeoModel:
         self._decode_states: Dict[tuple, SimpleNamespace] = {}
         self._build_structs()
         self.use_graph = os.environ.get("TEO_NO_GRAPH", "0") != "1"
+        self.retire_finished = os.environ.get("TEO_NO_RETIRE", "0") != "1"
         self.set_pdl(os.environ.get("TEO_NO_PDL", "0") != "1")
         self.last_timings: Dict[str, float] = {}
         self.decode_step_launches = 0          # counted on the eager step that precedes graph capture
@@ -241,6 +242,39 @@ class TeoModel:
             img_base += n_img
         return srcs, lens
 
+    # ------------------------------------------------------------------ decode state / step
+    RETIRE_FRACTION = 0.25          # compact the batch at a sync point once this share of its rows has finished
+
+    def _decode_state(self, B: int, shape_key: tuple, dws: torch.Tensor) -> SimpleNamespace:
+        """Device-resident state of the decode loop for one batch shape, with stable addresses so that the CUDA graph captured
+        over it is reused across calls (and across the compactions of one call).  A cached entry is dropped when what its
+        graph baked in has moved: the page pools (base pointer or pages per layer) or the workspace."""
+        max_new_tokens, max_pages = shape_key[0], shape_key[1]
+        l, dev = self.cfg.llama, self.device
+        key = (B, *shape_key, self.use_pdl)
+        pool_id = (self._kv_pool.data_ptr(), int(self._kv_pool.shape[1]))
+        st = self._decode_states.get(key)
+        if st is None or st.pool_id != pool_id or st.dws_ptr != dws.data_ptr():
+            with torch.inference_mode(False):     # cached across calls: must stay ordinary tensors (callers may use inference_mode)
+                st = SimpleNamespace(
+                    B=B, d_len=torch.empty(B, dtype=torch.int32, device=dev), d_bt=torch.empty(B * max_pages, dtype=torch.int32, device=dev),
+                    logits=torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev),
+                    finished=torch.empty(B, dtype=torch.uint8, device=dev), tokens=torch.empty(B, max_new_tokens, dtype=torch.int32, device=dev),
+                    next_ids=torch.empty(B, dtype=torch.int32, device=dev), step_ptr=torch.empty(1, dtype=torch.int32, device=dev),
+                    seed_dev=torch.empty(1, dtype=torch.int64, device=dev), graph=None, pool_id=pool_id, dws_ptr=dws.data_ptr())
+            self._decode_states.pop(key, None)
+            if len(self._decode_states) >= 8:
+                self._decode_states.pop(next(iter(self._decode_states)))
+            self._decode_states[key] = st
+        return st
+
+    def _decode_step(self, st: SimpleNamespace, shape_key: tuple, dws: torch.Tensor) -> None:
+        max_new_tokens, max_pages, total_len, eos = shape_key[:4]
+        L.check(self.lib.teo_llama_decode_step(self._h, C.byref(self._llama), st.next_ids.data_ptr(), st.d_len.data_ptr(),
+                                               st.finished.data_ptr(), st.tokens.data_ptr(), max_new_tokens, st.step_ptr.data_ptr(), st.B,
+                                               total_len, st.d_bt.data_ptr(), max_pages, st.logits.data_ptr(), eos, dws.data_ptr(),
+                                               dws.numel(), self._stream()), "teo_llama_decode_step")
+
     # ------------------------------------------------------------------ batched generation
     @torch.no_grad()
     def generate_batch(self, input_ids: Sequence[Sequence[int]], frames_u8: Optional[Sequence[torch.Tensor]] = None,
@@ -288,8 +322,11 @@ class TeoModel:
         if total_len > self.rope_max_pos:
             raise ValueError(f"context {total_len} exceeds RoPE table ({self.rope_max_pos})")
         ps = cfg.kv_page_size
-        pages_per = [_cdiv(n + max_new_tokens, ps) for n in lens]
-        max_pages = max(pages_per)
+        # page plan + allocation through the C-ABI (teo_kv_plan / teo_kv_alloc, csrc/kv_pages.cu)
+        lens_c, pages_c = (C.c_int * B)(*lens), (C.c_int * B)()
+        mx_c, tot_c = C.c_int(), C.c_int()
+        L.check(self.lib.teo_kv_plan(lens_c, B, max_new_tokens, ps, pages_c, C.byref(mx_c), C.byref(tot_c)), "teo_kv_plan")
+        pages_per, max_pages, n_pages = list(pages_c), mx_c.value, tot_c.value
         cu = np.zeros(B + 1, dtype=np.int32)
         cu[1:] = np.cumsum(lens)
         meta = np.empty(3 * T + (B + 1) + B + B + B * max_pages, dtype=np.int32)
@@ -307,12 +344,18 @@ class TeoModel:
         v_cu[:] = cu
         v_last[:] = cu[1:] - 1
         v_len[:] = lens
-        page0 = 0
         v_bt[:] = 0
-        for b in range(B):
-            v_bt[b, :pages_per[b]] = np.arange(page0, page0 + pages_per[b], dtype=np.int32)
-            page0 += pages_per[b]
-        self._ensure_kv(page0)
+        alloc = C.c_void_p()
+        L.check(self.lib.teo_kv_create(n_pages, C.byref(alloc)), "teo_kv_create")
+        try:
+            for b in range(B):
+                got = self.lib.teo_kv_alloc(alloc, lens[b] + max_new_tokens, ps, v_bt[b].ctypes.data_as(C.POINTER(C.c_int)), max_pages)
+                if got != pages_per[b]:
+                    L.check(got if got < 0 else -1, "teo_kv_alloc")
+        except Exception:
+            self.lib.teo_kv_destroy(alloc)
+            raise
+        self._ensure_kv(n_pages)
         meta_h = torch.from_numpy(meta).pin_memory()
         meta_d = meta_h.to(dev, non_blocking=True)
         d_src, d_pos, d_sid = meta_d[0:T], meta_d[T:2 * T], meta_d[2 * T:3 * T]
@@ -323,25 +366,10 @@ class TeoModel:
         d_bt0 = meta_d[o:o + B * max_pages]
         h = l.hidden_size
         # ---- per-shape decode state with stable addresses, so the captured decode graph is reused across calls
-        dwb = self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len)
-        dws = self._ws("decode", dwb)
-        # the seed is NOT part of the key: the captured step reads it from device memory (st.seed_dev)
-        key = (B, max_new_tokens, max_pages, total_len, eos, sampling, float(temperature or 0.0) if sampling else 0.0,
-               int(top_k) if sampling else 0, self.use_pdl)
-        st = self._decode_states.get(key)
-        # a captured graph bakes in the per-layer page-pool pointers (pool base + layer · n_pages · page bytes) and the workspace
-        pool_id = (self._kv_pool.data_ptr(), int(self._kv_pool.shape[1]))
-        if st is None or st.pool_id != pool_id or st.dws_ptr != dws.data_ptr():
-            with torch.inference_mode(False):     # cached across calls: must stay ordinary tensors (callers may use inference_mode)
-                st = SimpleNamespace(
-                    d_len=torch.empty(B, dtype=torch.int32, device=dev), d_bt=torch.empty(B * max_pages, dtype=torch.int32, device=dev),
-                    logits=torch.empty(B, l.vocab_size, dtype=torch.float32, device=dev),
-                    finished=torch.empty(B, dtype=torch.uint8, device=dev), tokens=torch.empty(B, max_new_tokens, dtype=torch.int32, device=dev),
-                    next_ids=torch.empty(B, dtype=torch.int32, device=dev), step_ptr=torch.empty(1, dtype=torch.int32, device=dev),
-                    seed_dev=torch.empty(1, dtype=torch.int64, device=dev), graph=None, pool_id=pool_id, dws_ptr=dws.data_ptr())
-            if len(self._decode_states) >= 4:
-                self._decode_states.pop(next(iter(self._decode_states)))
-            self._decode_states[key] = st
+        dws = self._ws("decode", self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), B, total_len))
+        shape_key = (max_new_tokens, max_pages, total_len, eos, sampling, float(temperature or 0.0) if sampling else 0.0,
+                     int(top_k) if sampling else 0)
+        st = self._decode_state(B, shape_key, dws)
         d_len, d_bt, logits = st.d_len, st.d_bt, st.logits
         finished, tokens, next_ids, step_ptr = st.finished, st.tokens, st.next_ids, st.step_ptr
         d_len.copy_(d_len0)
@@ -372,53 +400,82 @@ class TeoModel:
 
         _nvtx(None)
         _nvtx("teo.decode")
-        # ---- decode: one captured step, replayed (the graph is cached with the state above)
-        def step():
-            L.check(self.lib.teo_llama_decode_step(self._h, C.byref(self._llama), next_ids.data_ptr(), d_len.data_ptr(),
-                                                   finished.data_ptr(), tokens.data_ptr(), max_new_tokens, step_ptr.data_ptr(), B,
-                                                   total_len, d_bt.data_ptr(), max_pages, logits.data_ptr(), eos, dws.data_ptr(),
-                                                   dws.numel(), self._stream()), "teo_llama_decode_step")
-
+        # ---- decode: one captured step per batch shape, replayed; finished sequences are retired at the 32-step sync
         n_steps = max_new_tokens - 1
         done = 0
         use_graph = self.use_graph and not return_logits
-        if use_graph and st.graph is None and n_steps >= 5:
-            l0 = self.launch_count()
-            step()                      # first step eagerly (warms function attributes / tensor maps), then capture once
-            self.decode_step_launches = self.launch_count() - l0       # kernels in one decode step (= one graph replay)
-            done = 1
-            torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            cap_stream = torch.cuda.Stream(device=dev)
-            cap_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.graph(graph, stream=cap_stream):
-                step()
-            st.graph = graph
-        graph = st.graph if use_graph else None
         replays = 0
+        rows = list(range(B))                                   # original example index of every current batch row
+        result = np.full((B, max_new_tokens), -1, dtype=np.int32)
+        retired_pages = 0
         while done < n_steps:
-            if graph is not None:
-                graph.replay()
+            if use_graph and st.graph is None and n_steps - done >= 5:
+                l0 = self.launch_count()
+                self._decode_step(st, shape_key, dws)           # first step eagerly (warms function attributes / tensor maps), then capture once
+                self.decode_step_launches = self.launch_count() - l0       # kernels in one decode step (= one graph replay)
+                done += 1
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                cap_stream = torch.cuda.Stream(device=dev)
+                cap_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.graph(graph, stream=cap_stream):
+                    self._decode_step(st, shape_key, dws)
+                st.graph = graph
+                continue
+            if use_graph and st.graph is not None:
+                st.graph.replay()
                 replays += 1
             else:
-                step()
+                self._decode_step(st, shape_key, dws)
                 if return_logits:
-                    step_logits.append(logits.clone())
+                    step_logits.append(st.logits.clone())
             done += 1
-            if done % 32 == 0 and bool(finished.all()):     # one D2H sync every 32 tokens
-                break
+            if done % 32 == 0 and done < n_steps:               # one D2H sync every 32 tokens
+                fin = st.finished.cpu().numpy().astype(bool)
+                if fin.all():
+                    break
+                if self.retire_finished and not return_logits and fin.sum() >= self.RETIRE_FRACTION * len(rows):
+                    # Retire finished sequences (the reference stops each sample at its own </s>, inference.py:57-72): keep their
+                    # tokens, give their pages back (teo_kv_free) and continue with a compacted batch — a smaller decode state
+                    # (its own cached CUDA graph) whose rows are copies of the survivors' lengths, page tables and next ids.
+                    toks_now = st.tokens.cpu().numpy()
+                    bt_now = st.d_bt.view(len(rows), max_pages).cpu().numpy()
+                    keep = np.nonzero(~fin)[0]
+                    for r in np.nonzero(fin)[0]:
+                        result[rows[r]] = toks_now[r]
+                        npg = pages_per[rows[r]]
+                        pg = np.ascontiguousarray(bt_now[r, :npg], dtype=np.int32)
+                        L.check(self.lib.teo_kv_free(alloc, pg.ctypes.data_as(C.POINTER(C.c_int)), npg), "teo_kv_free")
+                        retired_pages += npg
+                    idx = torch.from_numpy(keep).to(dev)
+                    dws = self._ws("decode", self.lib.teo_llama_decode_workspace_bytes(C.byref(self._llama), len(keep), total_len))
+                    st2 = self._decode_state(len(keep), shape_key, dws)
+                    st2.d_len.copy_(st.d_len[idx])
+                    st2.d_bt.copy_(st.d_bt.view(len(rows), max_pages)[idx].reshape(-1))
+                    st2.next_ids.copy_(st.next_ids[idx])
+                    st2.tokens.copy_(st.tokens[idx])
+                    st2.finished.zero_()
+                    st2.step_ptr.copy_(st.step_ptr)
+                    st2.seed_dev.copy_(st.seed_dev)
+                    L.check(self.lib.teo_set_sampling_seed_device(self._h, st2.seed_dev.data_ptr()), "teo_set_sampling_seed_device")
+                    rows = [rows[r] for r in keep]
+                    st = st2
         if ev:
             ev[3].record()
-        toks = tokens.cpu().numpy()
+        toks = st.tokens.cpu().numpy()
+        for r, orig in enumerate(rows):
+            result[orig] = toks[r]
+        self.lib.teo_kv_destroy(alloc)
         _nvtx(None)
         if ev:
             torch.cuda.synchronize(dev)
             self.last_timings = {"vit_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
                                  "decode_ms": ev[2].elapsed_time(ev[3]), "frames": int(sum(per_sample)),
-                                 "prefill_tokens": T, "decode_steps": done, "batch": B, "graph_replays": replays}
+                                 "prefill_tokens": T, "decode_steps": done, "batch": B, "graph_replays": replays,
+                                 "final_batch": len(rows), "retired_pages": retired_pages}
         outs: List[List[int]] = []
         for b in range(B):
-            row = toks[b]
+            row = result[b]
             cut = len(row)
             neg = np.nonzero(row < 0)[0]
             if len(neg):

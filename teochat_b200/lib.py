@@ -75,6 +75,13 @@ _SIGS = {
     "teo_vit_drop_cls": (i, [vp, vp, i, i, i, vp]),
     "teo_flash_attention": (i, [vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, f, i, vp]),
     "teo_flash_attention_tc": (i, [vp, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, i, f, i, i, vp]),
+    "teo_kv_pool_bytes": (sz, [i, i, i, i, i]),
+    "teo_kv_plan": (i, [C.POINTER(i), i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+    "teo_kv_create": (i, [i, C.POINTER(vp)]),
+    "teo_kv_destroy": (i, [vp]),
+    "teo_kv_available": (i, [vp]),
+    "teo_kv_alloc": (i, [vp, i, i, C.POINTER(i), i]),
+    "teo_kv_free": (i, [vp, C.POINTER(i), i]),
     "teo_rope_kv_write": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]),
     "teo_decode_attention_workspace_bytes": (sz, [i, i, i, i]),
     "teo_decode_attention": (i, [vp, i, vp, vp, i, vp, vp, i, i, i, i, i, f, vp, sz, vp]),

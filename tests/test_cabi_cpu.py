@@ -82,3 +82,27 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_kv_page_planner_and_allocator(lib):
+    """teo_kv_plan / teo_kv_create / teo_kv_alloc / teo_kv_free (SURVEY.md §8b minimum set): host-only, so it runs without a GPU."""
+    lens = (C.c_int * 4)(130, 64, 1, 2130)
+    per, mx, tot = (C.c_int * 4)(), C.c_int(), C.c_int()
+    assert lib.teo_kv_plan(lens, 4, 256, 64, per, C.byref(mx), C.byref(tot)) == 0
+    assert list(per) == [7, 5, 5, 38] and mx.value == 38 and tot.value == 55         # ceil((len + 256) / 64)
+    assert lib.teo_kv_plan(lens, 4, 256, 0, per, None, None) != 0 and b"kv_plan" in lib.teo_last_error()
+    assert lib.teo_kv_pool_bytes(55, 32, 64, 128, 0) == 55 * 2 * 32 * 64 * 128 * 2
+    assert lib.teo_kv_pool_bytes(55, 32, 64, 128, 1) == 55 * 2 * 32 * 64 * 128 * 4
+    a = C.c_void_p()
+    assert lib.teo_kv_create(12, C.byref(a)) == 0 and lib.teo_kv_available(a) == 12
+    row = (C.c_int * 8)()
+    assert lib.teo_kv_alloc(a, 130 + 256, 64, row, 8) == 7 and list(row)[:7] == [0, 1, 2, 3, 4, 5, 6]      # lowest ids first
+    row2 = (C.c_int * 8)()
+    assert lib.teo_kv_alloc(a, 200, 64, row2, 8) == 4 and list(row2)[:4] == [7, 8, 9, 10]
+    assert lib.teo_kv_alloc(a, 129, 64, row2, 8) == -3 and lib.teo_kv_available(a) == 1         # exhausted: nothing taken
+    assert lib.teo_kv_alloc(a, 64 * 9, 64, row2, 8) == -1                                        # row too short for 9 pages
+    assert lib.teo_kv_free(a, row, 7) == 0 and lib.teo_kv_available(a) == 8
+    assert lib.teo_kv_free(a, row, 7) == -1                                                      # double free is rejected
+    row3 = (C.c_int * 8)()
+    assert lib.teo_kv_alloc(a, 3 * 64, 64, row3, 8) == 3 and list(row3)[:3] == [0, 1, 2]          # freed pages are reused
+    assert lib.teo_kv_destroy(a) == 0
