@@ -202,6 +202,11 @@ int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed)
  * that one captured CUDA graph of the step serves every seed; NULL switches back to the host value */
 int teo_set_sampling_seed_device(teo_handle* h, const void* seed_u64_device);
 
+/* teo_llama_decode_step runs the GEMMs between two attention calls (o_proj, gate/up, down, next qkv or lm_head, with their
+ * reductions) as ONE persistent kernel per layer (default on; TEO_DEC_CHAIN=0 in the environment or enabled = 0 selects the
+ * one-kernel-per-GEMM sequence).  Both produce bit-identical logits and ids. */
+int teo_set_decode_chain(teo_handle* h, int enabled);
+
 /* programmatic dependent launch between the kernels of teo_llama_decode_step (default on): each kernel's launch,
  * prologue and — for the GEMMs — weight prefetch overlap the tail of its predecessor.  Results are identical. */
 int teo_set_pdl(teo_handle* h, int enabled);

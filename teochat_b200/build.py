@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libteochat_b200.so")
-SOURCES = ["gemm.cu", "gemm_pair.cu", "attention.cu", "attention_tc.cu", "decode_attn_mma.cu", "kernels_misc.cu", "preprocess.cu", "exact.cu", "model_exact.cu", "kv_pages.cu", "model.cu"]
+SOURCES = ["gemm.cu", "gemm_pair.cu", "attention.cu", "attention_tc.cu", "decode_attn_mma.cu", "decode_chain.cu", "kernels_misc.cu", "preprocess.cu", "exact.cu", "model_exact.cu", "kv_pages.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

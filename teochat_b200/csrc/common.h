@@ -109,6 +109,8 @@ struct teo_handle {
     unsigned long long sample_seed = 0;
     const unsigned long long* sample_seed_ptr = nullptr;   // device-resident seed (teo_set_sampling_seed_device); wins over sample_seed
     bool pdl = true;                   // programmatic dependent launch inside teo_llama_decode_step (teo_set_pdl)
+    bool decode_chain = true;          // teo_llama_decode_step uses the persistent chain kernel (teo_set_decode_chain; TEO_DEC_CHAIN=0)
+    void* chain_sync = nullptr;        // 256 B of device memory: grid-barrier counters of the decode chain kernel (decode_chain.cu)
     std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
 };
 
@@ -157,6 +159,29 @@ int launch_argmax_step(const float* logits, int vocab, uint8_t* finished, int* t
 int launch_sample_step(const float* logits, int vocab, float temperature, int top_k, unsigned long long seed, uint8_t* finished, int* tokens,
                        int max_new, int step_host, int* step_ptr, int* next_ids, int* seq_lens, int n_seqs, int eos_id, cudaStream_t stream,
                        const unsigned long long* seed_ptr = nullptr);
+
+// Persistent decode chain kernel (decode_chain.cu): one launch runs up to four weight-streaming GEMM phases with their fused
+// reductions.  One ChainSpec per phase: weights (blocked layout), activations [B, K] (row stride lda), reduction + operands.
+struct ChainSpec {
+    const void* W;
+    int N, K;
+    const bf16* A;
+    int lda;
+    int reduce;                 // 0 residual + RMSNorm, 1 SwiGLU, 2 RoPE + KV write, 3 logits
+    bf16* x;
+    const bf16* norm_w;
+    bf16* y;
+    bf16* act;
+    bf16* qkv;
+    bf16* kv_pages;
+    float* logits;
+};
+bool decode_chain_enabled();
+bool decode_chain_shape_ok(int B, int hidden, int inter, int vocab, int n_heads);
+size_t decode_chain_workspace_bytes(int B, int N, int K, int grid);
+int launch_decode_chain(teo_handle* h, const ChainSpec* specs, int n_phases, int B, const int* positions, const int* block_table, int max_pages,
+                        int n_heads, int head_dim, int page_size, int inter, int interleaved, const float* rope_cos, const float* rope_sin,
+                        float eps, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // Small-M (decode) GEMM that stops at the fp32 partials; the consumer kernel reduces them (fixed slot order).
 int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,

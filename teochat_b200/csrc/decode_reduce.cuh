@@ -1,0 +1,222 @@
+// Reductions of the decode GEMMs' fp32 stream-K partials fused with the next element-wise stage (SwiGLU, RoPE + KV-page write,
+// residual + RMSNorm, logits), as __device__ functions: the stand-alone glue kernels of kernels_misc.cu and the persistent
+// decode chain kernel (decode_chain.cu) run the SAME code, so both decode paths produce bit-identical results.
+// Fixed summation order s = 0,1,… over the partial slots everywhere (deterministic).
+#pragma once
+#include "common.h"
+#include "ptx.cuh"
+
+namespace teo {
+
+// Column of gate value i of a [rows, 2·inter] gate/up row: [gate | up] halves, or interleaved in blocks of 32
+// (| gate 32 | up 32 |, TEO_ACT_SWIGLU_PAIRS layout); the matching up value sits `up_off` columns further.
+__device__ __forceinline__ long long gate_col(long long c, int interleaved) { return interleaved ? (c / 32) * 64 + (c % 32) : c; }
+
+// Σ_s P[s][idx] in the fixed order s = 0,1,…; loads are issued four at a time so the L2 latencies overlap.
+__device__ __forceinline__ float sum_partials_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
+    float acc = 0.f;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+        const float p0 = P[(s + 0) * stride + idx], p1 = P[(s + 1) * stride + idx];
+        const float p2 = P[(s + 2) * stride + idx], p3 = P[(s + 3) * stride + idx];
+        acc += p0; acc += p1; acc += p2; acc += p3;
+    }
+    for (; s < splits; ++s) acc += P[s * stride + idx];
+    return acc;
+}
+__device__ __forceinline__ float4 sum_partials4_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+        const float4 p0 = *reinterpret_cast<const float4*>(P + (s + 0) * stride + idx);
+        const float4 p1 = *reinterpret_cast<const float4*>(P + (s + 1) * stride + idx);
+        const float4 p2 = *reinterpret_cast<const float4*>(P + (s + 2) * stride + idx);
+        const float4 p3 = *reinterpret_cast<const float4*>(P + (s + 3) * stride + idx);
+        acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+        acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
+        acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
+        acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+    }
+    for (; s < splits; ++s) {
+        const float4 p = *reinterpret_cast<const float4*>(P + s * stride + idx);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    return acc;
+}
+
+// idx = row·cols + col; the slot count depends on the 128-column tile of `col`
+__device__ __forceinline__ float sum_partials(const PartialInfo& pi, long long idx, int col) {
+    return sum_partials_n(pi.P, pi.stride, partial_count(pi, col), idx);
+}
+__device__ __forceinline__ float4 sum_partials4(const PartialInfo& pi, long long idx, int col) {
+    return sum_partials4_n(pi.P, pi.stride, partial_count(pi, col), idx);
+}
+
+// act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i]); thread `tid` of `nthreads`
+__device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* __restrict__ act, int rows, int inter, int interleaved,
+                                                   long long tid, long long nthreads) {
+    const int i4 = inter / 4;
+    const int up_off = interleaved ? 32 : inter;
+    const long long total = static_cast<long long>(rows) * i4;
+    for (long long i = tid; i < total; i += nthreads) {
+        const long long r = i / i4, c = (i % i4) * 4;
+        const long long gc = gate_col(c, interleaved);
+        const float4 g = sum_partials4(pi, r * 2 * inter + gc, static_cast<int>(gc));
+        const float4 u = sum_partials4(pi, r * 2 * inter + gc + up_off, static_cast<int>(gc + up_off));
+        const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gg = __bfloat162float(__float2bfloat16_rn(gf[j])), uu = __bfloat162float(__float2bfloat16_rn(uf[j]));
+            o[j] = (gg / (1.0f + expf(-gg))) * uu;
+        }
+        *reinterpret_cast<uint2*>(act + r * inter + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    }
+}
+
+// One warp per (sequence, head) — `gw` of n_seqs·n_heads: reduce the q/k/v partials, RoPE q and k, write q into the qkv buffer
+// and k, v into the KV page of position positions[seq].
+__device__ __forceinline__ void reduce_rope_kv_warp(const PartialInfo& pi, bf16* __restrict__ qkv, const int* __restrict__ positions,
+                                                    bf16* __restrict__ kv_pages, const int* __restrict__ block_table, int max_pages,
+                                                    int n_seqs, int n_heads, int head_dim, int page_size,
+                                                    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int gw, int lane) {
+    if (gw >= n_seqs * n_heads) return;
+    const int seq = gw / n_heads, head = gw % n_heads;
+    const int hidden = n_heads * head_dim, half = head_dim / 2;
+    const int pos = positions[seq];
+    const int page = block_table[static_cast<size_t>(seq) * max_pages + pos / page_size];
+    const int slot = pos % page_size;
+    const long long rowbase = static_cast<long long>(seq) * 3 * hidden + head * head_dim;
+    bf16* q = qkv + rowbase;
+    bf16* kdst = kv_pages + (((static_cast<size_t>(page) * 2 + 0) * n_heads + head) * page_size + slot) * head_dim;
+    bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim;
+    const float* cs = rope_cos + static_cast<size_t>(pos) * half;
+    const float* sn = rope_sin + static_cast<size_t>(pos) * half;
+    const float* P = pi.P;
+    const long long stride = pi.stride;
+    const long long row0 = static_cast<long long>(seq) * 3 * hidden;
+    // head_dim-aligned head slices never straddle a 128-column tile when head_dim divides 128 or is a multiple of it
+    const int col_q = static_cast<int>(rowbase - row0);
+    const int cnt_q = partial_count(pi, col_q), cnt_k = partial_count(pi, col_q + hidden);
+    const bool uniform = (head_dim <= 128) && (128 % head_dim == 0);
+    auto r2 = [&](long long off, float& a, float& b, int cnt_hint) {   // two adjacent reduced values, rounded to bf16 like the GEMM output
+        float x0 = 0.f, x1 = 0.f;
+        const int splits = uniform ? cnt_hint : partial_count(pi, static_cast<int>(off - row0));
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {
+            const float2 p0 = *reinterpret_cast<const float2*>(P + (sp + 0) * stride + off);
+            const float2 p1 = *reinterpret_cast<const float2*>(P + (sp + 1) * stride + off);
+            const float2 p2 = *reinterpret_cast<const float2*>(P + (sp + 2) * stride + off);
+            const float2 p3 = *reinterpret_cast<const float2*>(P + (sp + 3) * stride + off);
+            x0 += p0.x; x1 += p0.y; x0 += p1.x; x1 += p1.y; x0 += p2.x; x1 += p2.y; x0 += p3.x; x1 += p3.y;
+        }
+        for (; sp < splits; ++sp) {
+            const float2 p = *reinterpret_cast<const float2*>(P + sp * stride + off);
+            x0 += p.x; x1 += p.y;
+        }
+        a = __bfloat162float(__float2bfloat16_rn(x0));
+        b = __bfloat162float(__float2bfloat16_rn(x1));
+    };
+    // All loads of an iteration are issued before its first store (the compiler cannot prove that the stores into qkv /
+    // the KV page do not alias the partials, so interleaving them would serialise five L2 round trips per thread).
+    for (int i = lane * 2; i < half; i += 64) {
+        const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
+        float qa0, qa1, qb0, qb1, ka0, ka1, kb0, kb1;
+        r2(rowbase + i, qa0, qa1, cnt_q);
+        r2(rowbase + i + half, qb0, qb1, cnt_q);
+        r2(rowbase + hidden + i, ka0, ka1, cnt_k);
+        r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int vi = 2 * i;                                   // lane·4: this lane's four v columns of the same pass
+        const bool has_v = vi < head_dim;
+        if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
+        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(qa0 * c0 - qb0 * s0, qa1 * c1 - qb1 * s1);
+        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(qb0 * c0 + qa0 * s0, qb1 * c1 + qa1 * s1);
+        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(ka0 * c0 - kb0 * s0, ka1 * c1 - kb1 * s1);
+        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(kb0 * c0 + ka0 * s0, kb1 * c1 + ka1 * s1);
+        if (has_v) *reinterpret_cast<uint2*>(vdst + vi) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+// x[row] = bf16(Σ partials + x[row]);  y[row] = RMSNorm(x[row]) · w — one row by 256 threads (8 warps) of one CTA, reproducing
+// BIT FOR BIT the summation tree of reduce_residual_rmsnorm_kernel (kernels_misc.cu: a cluster of 8 CTAs × 128 threads per
+// row, CTA r owning columns [r·d/8, (r+1)·d/8)): warp w here plays CTA rank w, and walks that CTA's four warps one after the
+// other — per-thread sums over its ≤ 2 float4 groups, xor-butterfly over the 32 lanes, the four warp sums added in order,
+// the eight CTA sums added in order.  `t256` = thread index in the 256-thread group, `cta_part` = 8 floats of shared memory;
+// `sync256` synchronises exactly those 256 threads.
+template <typename Sync>
+__device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& pi, bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                            bf16* __restrict__ y, int row, int d, float eps, int t256, float* cta_part,
+                                                            Sync sync256) {
+    constexpr int VC = 8, VT = 128, MAXV = 2;            // the stand-alone kernel's RN_CLUSTER, RN_THREADS, RN_MAXV
+    const int rank = t256 >> 5, lane = t256 & 31;
+    const int cols = d / VC;
+    const long long base = static_cast<long long>(row) * d + static_cast<long long>(rank) * cols;
+    float vals[4][MAXV][4];
+    uint2 wreg[4][MAXV];
+    float parts[4];
+#pragma unroll
+    for (int vw = 0; vw < 4; ++vw) {
+        const int vt = vw * 32 + lane;                   // thread index inside the emulated CTA
+        float sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int c = (v * VT + vt) * 4;
+            if (c < cols) {
+                const uint2 r = *reinterpret_cast<const uint2*>(x + base + c);
+                wreg[vw][v] = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
+                const float4 acc = sum_partials4(pi, base + c, rank * cols + c);
+                vals[vw][v][0] = __bfloat162float(__float2bfloat16_rn(acc.x + bf16_lo(r.x)));
+                vals[vw][v][1] = __bfloat162float(__float2bfloat16_rn(acc.y + bf16_hi(r.x)));
+                vals[vw][v][2] = __bfloat162float(__float2bfloat16_rn(acc.z + bf16_lo(r.y)));
+                vals[vw][v][3] = __bfloat162float(__float2bfloat16_rn(acc.w + bf16_hi(r.y)));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sq += vals[vw][v][j] * vals[vw][v][j];
+            }
+        }
+        parts[vw] = warp_sum(sq);
+    }
+    if (lane == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t += parts[i];
+        cta_part[rank] = t;
+    }
+    sync256();
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < VC; ++r) tot += cta_part[r];
+    sync256();                                           // cta_part may be rewritten by the next row
+    const float rstd = 1.0f / sqrtf(tot / static_cast<float>(d) + eps);
+#pragma unroll
+    for (int vw = 0; vw < 4; ++vw) {
+        const int vt = vw * 32 + lane;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int c = (v * VT + vt) * 4;
+            if (c < cols) {
+                const uint2 wv = wreg[vw][v];
+                const float wf[4] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y)};
+                const float* vv = vals[vw][v];
+                *reinterpret_cast<uint2*>(x + base + c) = make_uint2(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]));
+                *reinterpret_cast<uint2*>(y + base + c) = make_uint2(pack_bf16x2((vv[0] * rstd) * wf[0], (vv[1] * rstd) * wf[1]),
+                                                                     pack_bf16x2((vv[2] * rstd) * wf[2], (vv[3] * rstd) * wf[3]));
+            }
+        }
+    }
+}
+
+// out[i] = Σ_s P[s][i]  (fp32 logits: the reduction splitk_reduce_kernel does for the lm_head GEMM); thread `tid` of `nthreads`
+__device__ __forceinline__ void reduce_logits_part(const PartialInfo& pi, float* __restrict__ out, int rows, int cols, long long tid,
+                                                   long long nthreads) {
+    const long long total = static_cast<long long>(rows) * cols;
+    for (long long i = tid; i < total; i += nthreads) {
+        const int c = static_cast<int>(i % cols);
+        const int n = partial_count(pi, c);
+        float acc = 0.f;
+        for (int s = 0; s < n; ++s) acc += pi.P[s * pi.stride + i];
+        out[i] = acc;
+    }
+}
+
+}  // namespace teo

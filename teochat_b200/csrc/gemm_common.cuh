@@ -39,6 +39,7 @@ struct GemmArgs {
                                 // activation operand then holds K/k_wrap/64 bf16 planes side by side (exact mode: an fp32
                                 // activation split into hi | mid | lo bf16 terms, all multiplied by the same weights)
     int residual_f32;           // residual is float (direct-store epilogue only)
+    int group_n, raster, l2_hint;   // CTA-pair kernel: supertile width (tile columns), supertile order, L2 eviction hints (gemm_pair.cu)
     unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 

@@ -39,14 +39,34 @@ constexpr int PAIR_GROUP_M = 16;                                        // 256-r
 struct PairTile {
     int m2, n_blk;
 };
-// tile `unit` of the (num_m2 × num_n) grid, rasterised in groups of `group_m` tile rows, M fastest inside a group
-__device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n, int group_m) {
-    const int group_sz = group_m * num_n;
-    const int grp = unit / group_sz;
-    const int first = grp * group_m;
-    const int gm = min(group_m, num_m2 - first);
-    const int in_grp = unit - grp * group_sz;
-    return {first + in_grp % gm, in_grp / gm};
+// Tile `unit` of the (num_m2 × num_n) grid.  Supertiles of group_m tile rows × group_n tile columns, M fastest inside one.
+//   raster 0  supertiles walk along N inside a band of group_m rows, band after band: the band's A panel (group_m · 256 rows)
+//             is what should stay in L2 while W streams past it (group_n ≥ num_n is the one-dimensional grouping of round 1)
+//   raster 1  supertiles walk along M inside a strip of group_n columns, strip after strip: the strip's W panel stays, A streams
+__device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n, int group_m, int group_n, int raster) {
+    if (raster == 0) {
+        const int band_sz = group_m * num_n;
+        const int band = unit / band_sz;
+        const int first_m = band * group_m;
+        const int gm = min(group_m, num_m2 - first_m);
+        const int in_band = unit - band * band_sz;
+        const int per_sup = gm * group_n;
+        const int sn = in_band / per_sup;
+        const int first_n = sn * group_n;
+        const int in_sup = in_band - sn * per_sup;
+        return {first_m + in_sup % gm, first_n + in_sup / gm};
+    }
+    const int strip_sz = group_n * num_m2;
+    const int strip = unit / strip_sz;
+    const int first_n = strip * group_n;
+    const int gn = min(group_n, num_n - first_n);
+    const int in_strip = unit - strip * strip_sz;
+    const int per_sup = group_m * gn;
+    const int sm = in_strip / per_sup;
+    const int first_m = sm * group_m;
+    const int gm = min(group_m, num_m2 - first_m);
+    const int in_sup = in_strip - sm * per_sup;
+    return {first_m + in_sup % gm, first_n + in_sup / gm};
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -106,15 +126,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             pdl_wait();
             int s = 0;
             uint32_t ph = 0;
+            // L2 eviction priorities (l2_hint 1): the operand whose panel is meant to stay resident across the supertiles of a band /
+            // strip is fetched evict_last, the operand that streams past it evict_first
+            const uint64_t hint_a = g.l2_hint ? (g.raster == 0 ? L2_EVICT_LAST : L2_EVICT_FIRST) : L2_EVICT_NORMAL;
+            const uint64_t hint_w = g.l2_hint ? (g.raster == 0 ? L2_EVICT_FIRST : L2_EVICT_LAST) : L2_EVICT_NORMAL;
             for (int unit = pair; unit < units; unit += n_pairs) {
-                const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q);
+                const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
                 const int m_blk = t.m2 * 2 + rank;
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
-                    tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
-                    if (g.w_blocked) tma_load_4d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank);
-                    else tma_load_2d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2));
+                    if (g.l2_hint) {
+                        tma_load_2d_pair_hint(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM, hint_a);
+                        if (g.w_blocked) tma_load_4d_pair_hint(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank, hint_w);
+                        else tma_load_2d_pair_hint(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2), hint_w);
+                    } else {
+                        tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
+                        if (g.w_blocked) tma_load_4d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank);
+                        else tma_load_2d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2));
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -157,7 +187,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         int as = 0;
         uint32_t aph = 0;
         for (int unit = pair; unit < units; unit += n_pairs) {
-            const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q);
+            const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -183,6 +213,15 @@ bool gemm_pair_enabled() {
     return on;
 }
 
+// development hook (tools/pair_sweep.py): overrides of group_m, group_n, raster, l2_hint for the next launches; <= 0 / < 0 = default
+static int g_pair_cfg[4] = {0, 0, -1, -1};
+extern "C" void teo_dbg_pair_cfg(int group_m, int group_n, int raster, int l2_hint) {
+    g_pair_cfg[0] = group_m;
+    g_pair_cfg[1] = group_n;
+    g_pair_cfg[2] = raster;
+    g_pair_cfg[3] = l2_hint;
+}
+
 // Called by launch_gemm with the tensor maps already built: ta = A boxes of 128 rows, tb = W boxes of 128 rows (or the
 // 4-D blocked map with one 128-row block per box), tc / tr = 32-row boxes of C and of the residual.
 int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
@@ -198,12 +237,27 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
     // power — the prefill GEMMs run power-capped) until the A panels of a group no longer stay in L2 beside the W stream.
     // Measured in the full step on one box: 8 rows 869 ms of prefill, 12 849, 16 841, 20 / 24 / 32 slower again; a K-dependent
     // rule (≈ 32 MiB of A panels) was no better than the constant.  TEO_PAIR_GROUP_M=n overrides (A/B measurements).
-    static const int group_m = [] {
+    static const int env_group_m = [] {
         const char* e = getenv("TEO_PAIR_GROUP_M");
         return e ? std::max(1, atoi(e)) : PAIR_GROUP_M;
     }();
+    static const int env_group_n = [] {
+        const char* e = getenv("TEO_PAIR_GROUP_N");
+        return e ? std::max(1, atoi(e)) : (1 << 20);
+    }();
+    static const int env_raster = [] {
+        const char* e = getenv("TEO_PAIR_RASTER");
+        return e ? atoi(e) : 0;
+    }();
+    static const int env_hint = [] {
+        const char* e = getenv("TEO_PAIR_L2_HINT");
+        return e ? atoi(e) : 0;
+    }();
     GemmArgs ga = g;
-    ga.sk_q = group_m;                                   // (stream-K field, unused by this kernel: carries the group size)
+    ga.sk_q = g_pair_cfg[0] > 0 ? g_pair_cfg[0] : env_group_m;      // (stream-K field, unused by this kernel: carries the group size)
+    ga.group_n = g_pair_cfg[1] > 0 ? g_pair_cfg[1] : env_group_n;
+    ga.raster = g_pair_cfg[2] >= 0 ? g_pair_cfg[2] : env_raster;
+    ga.l2_hint = g_pair_cfg[3] >= 0 ? g_pair_cfg[3] : env_hint;
     TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, ta, tb, tc, tr, ga));
     TEO_LAUNCH_CHECK("gemm_pair_kernel");
     h->launches++;

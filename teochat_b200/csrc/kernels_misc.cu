@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "decode_reduce.cuh"
 #include "ptx.cuh"
 
 namespace teo {
@@ -228,10 +229,6 @@ __global__ void drop_cls_kernel(const uint4* __restrict__ hidden, uint4* __restr
     }
 }
 
-// Column of gate value i of a [rows, 2·inter] gate/up row: [gate | up] halves, or interleaved in blocks of 32
-// (| gate 32 | up 32 |, TEO_ACT_SWIGLU_PAIRS layout); the matching up value sits `up_off` columns further.
-__device__ __forceinline__ long long gate_col(long long c, int interleaved) { return interleaved ? (c / 32) * 64 + (c % 32) : c; }
-
 __global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict__ out, int rows, int inter, int interleaved) {
     const int i8 = inter / 8;
     const int up_off = interleaved ? 32 : inter;
@@ -371,46 +368,6 @@ rope_kv_write_vec_kernel(bf16* __restrict__ qkv, const int* __restrict__ positio
 // The decode GEMMs (M = batch) leave fp32 split-K partials P[s][rows][n]; these kernels reduce them in the
 // fixed order s = 0,1,… and do the next element-wise stage in the same pass (same rounding points as the
 // unfused chain: the reduced value is rounded to bf16 exactly where the GEMM epilogue would have).
-// Σ_s P[s][idx] in the fixed order s = 0,1,…; loads are issued four at a time so the L2 latencies overlap.
-__device__ __forceinline__ float sum_partials_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
-    float acc = 0.f;
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {
-        const float p0 = P[(s + 0) * stride + idx], p1 = P[(s + 1) * stride + idx];
-        const float p2 = P[(s + 2) * stride + idx], p3 = P[(s + 3) * stride + idx];
-        acc += p0; acc += p1; acc += p2; acc += p3;
-    }
-    for (; s < splits; ++s) acc += P[s * stride + idx];
-    return acc;
-}
-__device__ __forceinline__ float4 sum_partials4_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {
-        const float4 p0 = *reinterpret_cast<const float4*>(P + (s + 0) * stride + idx);
-        const float4 p1 = *reinterpret_cast<const float4*>(P + (s + 1) * stride + idx);
-        const float4 p2 = *reinterpret_cast<const float4*>(P + (s + 2) * stride + idx);
-        const float4 p3 = *reinterpret_cast<const float4*>(P + (s + 3) * stride + idx);
-        acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
-        acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
-        acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
-        acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
-    }
-    for (; s < splits; ++s) {
-        const float4 p = *reinterpret_cast<const float4*>(P + s * stride + idx);
-        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
-    return acc;
-}
-
-// idx = row·cols + col; the slot count depends on the 128-column tile of `col`
-__device__ __forceinline__ float sum_partials(const PartialInfo& pi, long long idx, int col) {
-    return sum_partials_n(pi.P, pi.stride, partial_count(pi, col), idx);
-}
-__device__ __forceinline__ float4 sum_partials4(const PartialInfo& pi, long long idx, int col) {
-    return sum_partials4_n(pi.P, pi.stride, partial_count(pi, col), idx);
-}
-
 // x[row] = bf16(Σ partials + x[row]);  y[row] = RMSNorm(x[row]) * w      (o_proj / down_proj → next norm)
 // A thread-block cluster of RN_CLUSTER CTAs shares one row (bs=32 rows alone would occupy 32 of 148 SMs): each CTA
 // reduces d/RN_CLUSTER columns with 16-byte loads, the per-CTA sums of squares are exchanged through distributed
@@ -483,24 +440,8 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
 __global__ void reduce_swiglu_kernel(PartialInfo pi, bf16* __restrict__ act, int rows, int inter, int interleaved) {
     pdl_trigger();
     pdl_wait();
-    const int i4 = inter / 4;
-    const int up_off = interleaved ? 32 : inter;
-    const long long total = static_cast<long long>(rows) * i4;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / i4, c = (i % i4) * 4;
-        const long long gc = gate_col(c, interleaved);
-        const float4 g = sum_partials4(pi, r * 2 * inter + gc, static_cast<int>(gc));
-        const float4 u = sum_partials4(pi, r * 2 * inter + gc + up_off, static_cast<int>(gc + up_off));
-        const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float gg = __bfloat162float(__float2bfloat16_rn(gf[j])), uu = __bfloat162float(__float2bfloat16_rn(uf[j]));
-            o[j] = (gg / (1.0f + expf(-gg))) * uu;
-        }
-        *reinterpret_cast<uint2*>(act + r * inter + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
-    }
+    reduce_swiglu_part(pi, act, rows, inter, interleaved, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                       static_cast<long long>(gridDim.x) * blockDim.x);
 }
 
 // One warp per (sequence, head): reduce the q/k/v partials, RoPE q and k, write q into the qkv buffer and k, v
@@ -511,64 +452,8 @@ __global__ void reduce_rope_kv_write_kernel(PartialInfo pi, bf16* __restrict__ q
                                             int page_size, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin) {
     pdl_trigger();
     pdl_wait();
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= n_seqs * n_heads) return;
-    const int seq = gw / n_heads, head = gw % n_heads;
-    const int hidden = n_heads * head_dim, half = head_dim / 2;
-    const int pos = positions[seq];
-    const int page = block_table[static_cast<size_t>(seq) * max_pages + pos / page_size];
-    const int slot = pos % page_size;
-    const long long rowbase = static_cast<long long>(seq) * 3 * hidden + head * head_dim;
-    bf16* q = qkv + rowbase;
-    bf16* kdst = kv_pages + (((static_cast<size_t>(page) * 2 + 0) * n_heads + head) * page_size + slot) * head_dim;
-    bf16* vdst = kv_pages + (((static_cast<size_t>(page) * 2 + 1) * n_heads + head) * page_size + slot) * head_dim;
-    const float* cs = rope_cos + static_cast<size_t>(pos) * half;
-    const float* sn = rope_sin + static_cast<size_t>(pos) * half;
-    const float* P = pi.P;
-    const long long stride = pi.stride;
-    const long long row0 = static_cast<long long>(seq) * 3 * hidden;
-    // head_dim-aligned head slices never straddle a 128-column tile when head_dim divides 128 or is a multiple of it
-    const int col_q = static_cast<int>(rowbase - row0);
-    const int cnt_q = partial_count(pi, col_q), cnt_k = partial_count(pi, col_q + hidden);
-    const bool uniform = (head_dim <= 128) && (128 % head_dim == 0);
-    auto r2 = [&](long long off, float& a, float& b, int cnt_hint) {   // two adjacent reduced values, rounded to bf16 like the GEMM output
-        float x0 = 0.f, x1 = 0.f;
-        const int splits = uniform ? cnt_hint : partial_count(pi, static_cast<int>(off - row0));
-        int sp = 0;
-        for (; sp + 4 <= splits; sp += 4) {
-            const float2 p0 = *reinterpret_cast<const float2*>(P + (sp + 0) * stride + off);
-            const float2 p1 = *reinterpret_cast<const float2*>(P + (sp + 1) * stride + off);
-            const float2 p2 = *reinterpret_cast<const float2*>(P + (sp + 2) * stride + off);
-            const float2 p3 = *reinterpret_cast<const float2*>(P + (sp + 3) * stride + off);
-            x0 += p0.x; x1 += p0.y; x0 += p1.x; x1 += p1.y; x0 += p2.x; x1 += p2.y; x0 += p3.x; x1 += p3.y;
-        }
-        for (; sp < splits; ++sp) {
-            const float2 p = *reinterpret_cast<const float2*>(P + sp * stride + off);
-            x0 += p.x; x1 += p.y;
-        }
-        a = __bfloat162float(__float2bfloat16_rn(x0));
-        b = __bfloat162float(__float2bfloat16_rn(x1));
-    };
-    // All loads of an iteration are issued before its first store (the compiler cannot prove that the stores into qkv /
-    // the KV page do not alias the partials, so interleaving them would serialise five L2 round trips per thread).
-    for (int i = lane * 2; i < half; i += 64) {
-        const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
-        float qa0, qa1, qb0, qb1, ka0, ka1, kb0, kb1;
-        r2(rowbase + i, qa0, qa1, cnt_q);
-        r2(rowbase + i + half, qb0, qb1, cnt_q);
-        r2(rowbase + hidden + i, ka0, ka1, cnt_k);
-        r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int vi = 2 * i;                                   // lane·4: this lane's four v columns of the same pass
-        const bool has_v = vi < head_dim;
-        if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
-        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(qa0 * c0 - qb0 * s0, qa1 * c1 - qb1 * s1);
-        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(qb0 * c0 + qa0 * s0, qb1 * c1 + qa1 * s1);
-        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(ka0 * c0 - kb0 * s0, ka1 * c1 - kb1 * s1);
-        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(kb0 * c0 + ka0 * s0, kb1 * c1 + ka1 * s1);
-        if (has_v) *reinterpret_cast<uint2*>(vdst + vi) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    }
+    reduce_rope_kv_warp(pi, qkv, positions, kv_pages, block_table, max_pages, n_seqs, n_heads, head_dim, page_size, rope_cos, rope_sin,
+                        (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------ greedy argmax + stop rule

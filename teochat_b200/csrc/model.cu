@@ -111,10 +111,12 @@ extern "C" int teo_create(int device_id, teo_handle** out) {
     TEO_CHECK_ARG(h != nullptr, "teo_create: out of host memory");
     h->device = device_id;
     h->num_sms = prop.multiProcessorCount;
+    h->decode_chain = decode_chain_enabled();
     *out = h;
     return TEO_OK;
 }
 extern "C" int teo_destroy(teo_handle* h) {
+    if (h && h->chain_sync) cudaFree(h->chain_sync);
     delete h;
     return TEO_OK;
 }
@@ -128,6 +130,11 @@ extern "C" int teo_set_sampling(teo_handle* h, float temperature, int top_k, uin
 extern "C" int teo_set_sampling_seed_device(teo_handle* h, const void* seed_u64_device) {
     TEO_CHECK_ARG(h != nullptr, "teo_set_sampling_seed_device: null handle");
     h->sample_seed_ptr = static_cast<const unsigned long long*>(seed_u64_device);
+    return TEO_OK;
+}
+extern "C" int teo_set_decode_chain(teo_handle* h, int enabled) {
+    TEO_CHECK_ARG(h != nullptr, "teo_set_decode_chain: null handle");
+    h->decode_chain = enabled != 0;
     return TEO_OK;
 }
 extern "C" int teo_set_pdl(teo_handle* h, int enabled) {
@@ -388,9 +395,12 @@ extern "C" int teo_llama_prefill(teo_handle* h, const teo_llama_model* m, void* 
 // ------------------------------------------------------------------------------ LLaMA decode step
 struct DecodeWs {
     bf16 *x, *norm_out, *qkv, *attn, *gate_up, *act;
-    uint8_t *gemm_ws, *attn_ws;
-    size_t gemm_ws_bytes, attn_ws_bytes;
+    uint8_t *gemm_ws, *attn_ws, *chain_ws;
+    size_t gemm_ws_bytes, attn_ws_bytes, chain_ws_bytes;
 };
+static bool decode_chain_usable(const teo_llama_model* m, int B) {
+    return m->w_blocked && decode_chain_shape_ok(B, m->hidden, m->inter, m->vocab, m->heads);
+}
 static size_t decode_ws_layout(const teo_llama_model* m, int B, Arena& A, DecodeWs* w) {
     const size_t h = m->hidden, I = m->inter;
     DecodeWs t;
@@ -408,6 +418,14 @@ static size_t decode_ws_layout(const teo_llama_model* m, int B, Arena& A, Decode
     t.gemm_ws = A.take<uint8_t>(g);
     t.attn_ws_bytes = teo_decode_attention_workspace_bytes(B, m->heads, m->hidden / m->heads, 32);
     t.attn_ws = A.take<uint8_t>(t.attn_ws_bytes);
+    t.chain_ws_bytes = 0;
+    if (decode_chain_usable(m, B)) {       // partial regions of the four phases of one chain launch (148-CTA split: the upper bound)
+        const int hh = m->hidden, II = m->inter;
+        t.chain_ws_bytes = decode_chain_workspace_bytes(B, hh, hh, 148) + decode_chain_workspace_bytes(B, 2 * II, hh, 148) +
+                           decode_chain_workspace_bytes(B, hh, II, 148) +
+                           std::max(decode_chain_workspace_bytes(B, 3 * hh, hh, 148), decode_chain_workspace_bytes(B, m->vocab, hh, 148));
+    }
+    t.chain_ws = A.take<uint8_t>(t.chain_ws_bytes);
     if (w) *w = t;
     return A.off;
 }
@@ -446,6 +464,56 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
     TEO_TRY(teo_splice_embed(m->embed, nullptr, next_ids, w.x, n_seqs, hdim, stream));
     TEO_TRY(teo_rmsnorm(w.x, m->layer[0].in_norm, w.norm_out, n_seqs, hdim, m->eps, stream));
     h->launches += 2;
+    if (fused && h->decode_chain && decode_chain_usable(m, n_seqs) && h->num_sms <= 148) {
+        // ---- persistent chain: per layer ONE kernel for o → norm → gate/up → SwiGLU → down → norm → next qkv → RoPE/KV (or lm_head),
+        //      then the attention kernel(s); 3 launches per layer instead of 10 (decode_chain.cu)
+        const int* lens = static_cast<const int*>(seq_lens);
+        const int* bt = static_cast<const int*>(block_table);
+        const float* rc = static_cast<const float*>(m->rope_cos);
+        const float* rs = static_cast<const float*>(m->rope_sin);
+        auto qkv_spec = [&](int l) {
+            ChainSpec s{};
+            s.W = m->layer[l].qkv_w; s.N = 3 * hdim; s.K = hdim; s.A = w.norm_out; s.lda = hdim; s.reduce = 2;
+            s.qkv = w.qkv; s.kv_pages = static_cast<bf16*>(m->layer[l].kv_pages);
+            return s;
+        };
+        {
+            ChainSpec first = qkv_spec(0);
+            TEO_TRY(launch_decode_chain(h, &first, 1, n_seqs, lens, bt, max_pages, m->heads, hd, m->page_size, I, m->gate_up_interleaved, rc, rs,
+                                        m->eps, w.chain_ws, w.chain_ws_bytes, stream));
+        }
+        for (int l = 0; l < m->layers; ++l) {
+            const teo_llama_layer& L = m->layer[l];
+            const bool last = l + 1 == m->layers;
+            TEO_TRY(launch_decode_attention(h, w.qkv, 3 * hdim, static_cast<const bf16*>(L.kv_pages), bt, max_pages, lens, 1, w.attn, n_seqs,
+                                            m->heads, hd, m->page_size, max_seq_len, scale, w.attn_ws, w.attn_ws_bytes, stream));
+            ChainSpec sp[4] = {};
+            sp[0].W = L.o_w; sp[0].N = hdim; sp[0].K = hdim; sp[0].A = w.attn; sp[0].lda = hdim; sp[0].reduce = 0;
+            sp[0].x = w.x; sp[0].norm_w = static_cast<const bf16*>(L.post_norm); sp[0].y = w.norm_out;
+            sp[1].W = L.gate_up_w; sp[1].N = 2 * I; sp[1].K = hdim; sp[1].A = w.norm_out; sp[1].lda = hdim; sp[1].reduce = 1;
+            sp[1].act = w.act;
+            sp[2].W = L.down_w; sp[2].N = hdim; sp[2].K = I; sp[2].A = w.act; sp[2].lda = I; sp[2].reduce = 0;
+            sp[2].x = w.x; sp[2].norm_w = static_cast<const bf16*>(last ? m->final_norm : m->layer[l + 1].in_norm); sp[2].y = w.norm_out;
+            if (!last) {
+                sp[3] = qkv_spec(l + 1);
+            } else {
+                sp[3].W = m->lm_head; sp[3].N = m->vocab; sp[3].K = hdim; sp[3].A = w.norm_out; sp[3].lda = hdim; sp[3].reduce = 3;
+                sp[3].logits = static_cast<float*>(logits);
+            }
+            TEO_TRY(launch_decode_chain(h, sp, 4, n_seqs, lens, bt, max_pages, m->heads, hd, m->page_size, I, m->gate_up_interleaved, rc, rs,
+                                        m->eps, w.chain_ws, w.chain_ws_bytes, stream));
+        }
+        if (h->temperature > 0.f)
+            TEO_TRY(launch_sample_step(static_cast<const float*>(logits), m->vocab, h->temperature, h->top_k, h->sample_seed,
+                                       static_cast<uint8_t*>(finished), static_cast<int*>(tokens), max_new, 0, static_cast<int*>(step_ptr),
+                                       static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs, eos_id, stream, h->sample_seed_ptr));
+        else
+            TEO_TRY(launch_argmax_step(static_cast<const float*>(logits), m->vocab, static_cast<uint8_t*>(finished), static_cast<int*>(tokens),
+                                       max_new, 0, static_cast<int*>(step_ptr), static_cast<int*>(next_ids), static_cast<int*>(seq_lens), n_seqs,
+                                       eos_id, stream));
+        h->launches += 2;
+        return TEO_OK;
+    }
     for (int l = 0; l < m->layers; ++l) {
         const teo_llama_layer& L = m->layer[l];
         const void* next_norm = (l + 1 < m->layers) ? m->layer[l + 1].in_norm : m->final_norm;

@@ -96,6 +96,7 @@ _SIGS = {
     "teo_sample_step": (i, [vp, i, f, i, u64, vp, vp, i, i, vp, i, i, vp]),
     "teo_set_sampling": (i, [vp, f, i, u64]),
     "teo_set_sampling_seed_device": (i, [vp, vp]),
+    "teo_set_decode_chain": (i, [vp, i]),
     "teo_set_pdl": (i, [vp, i]),
     "teo_vit_workspace_bytes": (sz, [C.POINTER(VitModel), i]),
     "teo_vit_encode": (i, [vp, C.POINTER(VitModel), vp, vp, i, vp, vp, sz, vp]),

@@ -453,3 +453,35 @@ def test_full_size_single_image_batch64_properties(full):
     e0, e1 = _rel(l64[5, 0], l2[0, 0]), _rel(l64[5, 1], l2[0, 1])
     print(f"bs=64 vs bs=2, sample 5: prefill logits rel err {e0:.3e}, first decode step {e1:.3e}")
     assert e0 <= 8e-2 and e1 <= 8e-2
+
+
+@pytest.mark.parametrize("case", ["tiny_b5", "tiny_b40", "tiny_b100", "fullwidth_depth2_b3"])
+def test_decode_chain_bit_identical_to_kernel_per_gemm(case):
+    """The persistent decode chain kernel (decode_chain.cu: o_proj → norm → gate/up → SwiGLU → down → norm → next qkv / lm_head in
+    one launch per layer, grid barriers between the phases) against the one-kernel-per-GEMM sequence it replaces: same MMA
+    order, same reduction order → every step's logits and all ids BIT-identical, eager and graph-replayed, at the three
+    batch tile widths (BN = 32 / 64 / 128) and at full LLaMA-2-7B widths."""
+    from oracle import weights as OW
+    if case.startswith("tiny"):
+        cfg, B, n_new = TeoConfig.tiny(), int(case.split("_b")[1]), 12
+    else:
+        cfg, B, n_new = _full_width(2, 1), 3, 8
+    model = _model(cfg, 99)
+    ids = [[1, 17, -200, 5, 6, 30 + b % 7] + ([-200, 9] if b % 3 == 0 else []) for b in range(B)]
+    frames = [OW.synthetic_frames_u8(2 if b % 3 == 0 else 1, cfg.vision.image_size, 200 + b % 11) for b in range(B)]
+    model.set_decode_chain(True)
+    ids_c, lg_c = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1, return_logits=True)
+    graph_c = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1)
+    launches_c = model.decode_step_launches
+    model.set_decode_chain(False)
+    ids_k, lg_k = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1, return_logits=True)
+    graph_k = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1)
+    launches_k = model.decode_step_launches
+    model.set_decode_chain(True)
+    assert torch.isfinite(lg_c).all()
+    assert torch.equal(lg_c, lg_k), f"max |diff| {(lg_c - lg_k).abs().max().item():.3e}"
+    assert ids_c == ids_k == graph_c == graph_k
+    print(f"{case}: kernels per decode step {launches_c} (chain) vs {launches_k} (per GEMM)")
+    assert launches_c < launches_k
+    del model
+    torch.cuda.empty_cache()
