@@ -63,7 +63,16 @@ struct ChainArgs {
     const float* rope_cos;
     const float* rope_sin;
     float eps;
+    int l2_prefetch;            // weight k-blocks (16 KiB each) per CTA the producer prefetches into L2 while it waits for a phase's input
+    unsigned long long* trace;  // development only (teo_dbg_chain_trace): per CTA and phase 8 %globaltimer stamps, else nullptr
 };
+__device__ __forceinline__ void chain_stamp(const ChainArgs& a, int phase, int slot) {
+    if (a.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.trace[(static_cast<size_t>(blockIdx.x) * CH_MAX_PHASES + phase) * 8 + slot] = t;
+    }
+}
 
 template <int BN>
 struct ChainCfg {
@@ -180,12 +189,22 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tw0, const __grid_consta
                     load_w(s, k);
                     if (++s == STAGES) { s = 0; ph_bit ^= 1; }
                 }
+                chain_stamp(a, p, 0);            // ring filled with this phase's first weight tiles
+                // HBM would idle until the phase's input exists (the grid barrier + the reduction before it): pull the next
+                // weight k-blocks of this CTA's share into L2 meanwhile, so that the stream restarts at L2 speed
+                if (p > 0 || a.l2_prefetch < 0) {
+                    const int npf = a.l2_prefetch < 0 ? -a.l2_prefetch : a.l2_prefetch;
+                    for (long long k = k0 + pre; k < k1 && k < k0 + pre + npf; ++k)
+                        tma_prefetch_l2_4d(tw[p], 0, 0, static_cast<int>(k % total_kb), static_cast<int>(k / total_kb));
+                }
+                chain_stamp(a, p, 1);            // L2 prefetches issued
                 if (p == 0) {
                     pdl_wait();
                 } else {
                     grid_wait(&a.sync[2 * (p - 1) + 1], G);
                     asm volatile("fence.proxy.async;" ::: "memory");        // other CTAs' generic-proxy stores → this thread's TMA reads
                 }
+                chain_stamp(a, p, 2);            // input of the phase complete
                 {
                     int st = s0;
                     for (int i = 0; i < pre; ++i) {
@@ -279,8 +298,10 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tw0, const __grid_consta
             // ---- all partials of the phase complete, everywhere
             epi_bar_sync();
             if (t256 == 0) {
+                chain_stamp(a, p, 3);            // this CTA's partials stored
                 grid_arrive(&a.sync[2 * p]);
                 grid_wait(&a.sync[2 * p], G);
+                chain_stamp(a, p, 4);            // everyone's partials stored
             }
             epi_bar_sync();
             // ---- the phase's reduction, spread over the epilogue warps of the whole grid
@@ -301,7 +322,12 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tw0, const __grid_consta
             // ---- the next phase's input complete, everywhere (the producer warps wait on this counter)
             if (p + 1 < a.n_phases) {
                 epi_bar_sync();
-                if (t256 == 0) grid_arrive(&a.sync[2 * p + 1]);
+                if (t256 == 0) {
+                    chain_stamp(a, p, 5);        // this CTA's part of the reduction done
+                    grid_arrive(&a.sync[2 * p + 1]);
+                }
+            } else if (t256 == 0) {
+                chain_stamp(a, p, 5);
             }
         }
     }
@@ -320,6 +346,24 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tw0, const __grid_consta
 }
 
 int get_tmap_wblocked(teo_handle* h, const void* ptr, uint64_t N, uint64_t K, uint32_t nblocks, CUtensorMap* out);
+
+// development hooks (tools/chain_trace.py): a device buffer of `launches` × 148 × 4 × 8 u64 stamped by the next chain launches
+// (used as a ring), and the L2-prefetch depth (k-blocks per CTA and phase; < 0: also before the first phase)
+static unsigned long long* g_chain_trace = nullptr;
+static int g_chain_trace_cap = 0;
+static long long g_chain_trace_n = 0;
+extern "C" long long teo_dbg_chain_trace(void* device_buffer, int launches) {
+    const long long n = g_chain_trace_n;
+    g_chain_trace = static_cast<unsigned long long*>(device_buffer);
+    g_chain_trace_cap = device_buffer ? launches : 0;
+    g_chain_trace_n = 0;
+    return n;
+}
+static int g_chain_pf = [] {
+    const char* e = getenv("TEO_CHAIN_PF");
+    return e ? atoi(e) : 24;
+}();
+extern "C" void teo_dbg_chain_prefetch(int kblocks) { g_chain_pf = kblocks; }
 
 bool decode_chain_enabled() {
     static const bool on = [] {
@@ -389,6 +433,9 @@ int launch_decode_chain(teo_handle* h, const ChainSpec* specs, int n_phases, int
     a.rope_cos = rope_cos;
     a.rope_sin = rope_sin;
     a.eps = eps;
+    a.l2_prefetch = g_chain_pf;
+    a.trace = (g_chain_trace && g_chain_trace_cap > 0)
+                  ? g_chain_trace + (g_chain_trace_n++ % g_chain_trace_cap) * (148ull * CH_MAX_PHASES * 8) : nullptr;
     CUtensorMap tw[CH_MAX_PHASES], ta[CH_MAX_PHASES];
     size_t off = 0;
     for (int p = 0; p < n_phases; ++p) {

@@ -153,23 +153,52 @@ __device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& p
     const int cols = d / VC;
     const long long base = static_cast<long long>(row) * d + static_cast<long long>(rank) * cols;
     float vals[4][MAXV][4];
-    uint2 wreg[4][MAXV];
+    uint2 wreg[4][MAXV], xreg[4][MAXV];
+    int cnt[4][MAXV];
+    int max_cnt = 0;
+    // all loads of the row slice first: x, w, then the partial slots with the slot loop OUTERMOST, so that the thread's (up to
+    // eight) column groups are in flight together — one L2 round trip per slot instead of one per (group, slot)
+#pragma unroll
+    for (int vw = 0; vw < 4; ++vw) {
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            const int c = (v * VT + vw * 32 + lane) * 4;
+            cnt[vw][v] = 0;
+            vals[vw][v][0] = vals[vw][v][1] = vals[vw][v][2] = vals[vw][v][3] = 0.f;
+            if (c < cols) {
+                xreg[vw][v] = *reinterpret_cast<const uint2*>(x + base + c);
+                wreg[vw][v] = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
+                cnt[vw][v] = partial_count(pi, rank * cols + c);
+                max_cnt = max(max_cnt, cnt[vw][v]);
+            }
+        }
+    }
+#pragma unroll 2
+    for (int s = 0; s < max_cnt; ++s) {
+#pragma unroll
+        for (int vw = 0; vw < 4; ++vw) {
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) {
+                if (s < cnt[vw][v]) {                    // same order s = 0,1,… per element as sum_partials4_n
+                    const int c = (v * VT + vw * 32 + lane) * 4;
+                    const float4 p = *reinterpret_cast<const float4*>(pi.P + s * pi.stride + base + c);
+                    vals[vw][v][0] += p.x; vals[vw][v][1] += p.y; vals[vw][v][2] += p.z; vals[vw][v][3] += p.w;
+                }
+            }
+        }
+    }
     float parts[4];
 #pragma unroll
     for (int vw = 0; vw < 4; ++vw) {
-        const int vt = vw * 32 + lane;                   // thread index inside the emulated CTA
         float sq = 0.f;
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
-            const int c = (v * VT + vt) * 4;
-            if (c < cols) {
-                const uint2 r = *reinterpret_cast<const uint2*>(x + base + c);
-                wreg[vw][v] = *reinterpret_cast<const uint2*>(w + static_cast<long long>(rank) * cols + c);
-                const float4 acc = sum_partials4(pi, base + c, rank * cols + c);
-                vals[vw][v][0] = __bfloat162float(__float2bfloat16_rn(acc.x + bf16_lo(r.x)));
-                vals[vw][v][1] = __bfloat162float(__float2bfloat16_rn(acc.y + bf16_hi(r.x)));
-                vals[vw][v][2] = __bfloat162float(__float2bfloat16_rn(acc.z + bf16_lo(r.y)));
-                vals[vw][v][3] = __bfloat162float(__float2bfloat16_rn(acc.w + bf16_hi(r.y)));
+            if (cnt[vw][v] > 0) {
+                const uint2 r = xreg[vw][v];
+                vals[vw][v][0] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][0] + bf16_lo(r.x)));
+                vals[vw][v][1] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][1] + bf16_hi(r.x)));
+                vals[vw][v][2] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][2] + bf16_lo(r.y)));
+                vals[vw][v][3] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][3] + bf16_hi(r.y)));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sq += vals[vw][v][j] * vals[vw][v][j];
             }
@@ -194,7 +223,7 @@ __device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& p
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
             const int c = (v * VT + vt) * 4;
-            if (c < cols) {
+            if (cnt[vw][v] > 0) {
                 const uint2 wv = wreg[vw][v];
                 const float wf[4] = {bf16_lo(wv.x), bf16_hi(wv.x), bf16_lo(wv.y), bf16_hi(wv.y)};
                 const float* vv = vals[vw][v];

@@ -128,8 +128,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t ph = 0;
             // L2 eviction priorities (l2_hint 1): the operand whose panel is meant to stay resident across the supertiles of a band /
             // strip is fetched evict_last, the operand that streams past it evict_first
-            const uint64_t hint_a = g.l2_hint ? (g.raster == 0 ? L2_EVICT_LAST : L2_EVICT_FIRST) : L2_EVICT_NORMAL;
-            const uint64_t hint_w = g.l2_hint ? (g.raster == 0 ? L2_EVICT_FIRST : L2_EVICT_LAST) : L2_EVICT_NORMAL;
+            // l2_hint 1: resident evict_last + streaming evict_first; 2: resident evict_last only; 3: streaming evict_first only
+            const uint64_t h_stay = (g.l2_hint == 1 || g.l2_hint == 2) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+            const uint64_t h_stream = (g.l2_hint == 1 || g.l2_hint == 3) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+            const uint64_t hint_a = g.raster == 0 ? h_stay : h_stream;
+            const uint64_t hint_w = g.raster == 0 ? h_stream : h_stay;
             for (int unit = pair; unit < units; unit += n_pairs) {
                 const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
                 const int m_blk = t.m2 * 2 + rank;

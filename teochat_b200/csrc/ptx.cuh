@@ -88,6 +88,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
         ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 prefetch of one box of a 4-D tensor map (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* desc, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(desc), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA stages its own 128 rows of A and
 // half of the B tile, the leader (cluster rank 0) issues the MMA, each CTA's TMEM receives its 128 accumulator rows.
