@@ -202,9 +202,10 @@ int teo_set_sampling(teo_handle* h, float temperature, int top_k, uint64_t seed)
  * that one captured CUDA graph of the step serves every seed; NULL switches back to the host value */
 int teo_set_sampling_seed_device(teo_handle* h, const void* seed_u64_device);
 
-/* teo_llama_decode_step runs the GEMMs between two attention calls (o_proj, gate/up, down, next qkv or lm_head, with their
- * reductions) as ONE persistent kernel per layer (default on; TEO_DEC_CHAIN=0 in the environment or enabled = 0 selects the
- * one-kernel-per-GEMM sequence).  Both produce bit-identical logits and ids. */
+/* teo_llama_decode_step can run the GEMMs between two attention calls (o_proj, gate/up, down, next qkv or lm_head, with their
+ * reductions) as ONE persistent kernel per layer with grid barriers between the phases (csrc/decode_chain.cu) instead of one
+ * kernel per GEMM + one per reduction.  Both produce bit-identical logits and ids; measured on B200 the chain is the slower
+ * of the two (profiles/r02_decode_chain.txt), so it is OFF by default: enabled != 0 (or TEO_DEC_CHAIN=1) selects it. */
 int teo_set_decode_chain(teo_handle* h, int enabled);
 
 /* programmatic dependent launch between the kernels of teo_llama_decode_step (default on): each kernel's launch,

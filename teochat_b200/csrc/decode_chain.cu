@@ -361,14 +361,18 @@ extern "C" long long teo_dbg_chain_trace(void* device_buffer, int launches) {
 }
 static int g_chain_pf = [] {
     const char* e = getenv("TEO_CHAIN_PF");
-    return e ? atoi(e) : 24;
+    return e ? atoi(e) : 0;          // measured: 24 / 48 k-blocks of L2 prefetch per stall made the step 1.5 / 2.8 % slower
 }();
 extern "C" void teo_dbg_chain_prefetch(int kblocks) { g_chain_pf = kblocks; }
 
+// Default OFF: measured on B200 (profiles/r02_decode_chain.txt) the chain is bit-identical to the per-GEMM sequence but 4–10 %
+// SLOWER per decode step — the grid barriers wait for the slowest of 148 weight streams in every phase (finish-time skew of
+// 12–44 µs per phase) and the in-kernel reductions run on 148 × 256 threads instead of the wide glue grids.  TEO_DEC_CHAIN=1 /
+// teo_set_decode_chain(h, 1) select it.
 bool decode_chain_enabled() {
     static const bool on = [] {
         const char* e = getenv("TEO_DEC_CHAIN");
-        return !(e && e[0] == '0');
+        return e && e[0] == '1';
     }();
     return on;
 }

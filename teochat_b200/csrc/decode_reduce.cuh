@@ -61,9 +61,24 @@ __device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* 
     for (long long i = tid; i < total; i += nthreads) {
         const long long r = i / i4, c = (i % i4) * 4;
         const long long gc = gate_col(c, interleaved);
-        const float4 g = sum_partials4(pi, r * 2 * inter + gc, static_cast<int>(gc));
-        const float4 u = sum_partials4(pi, r * 2 * inter + gc + up_off, static_cast<int>(gc + up_off));
-        const float gf[4] = {g.x, g.y, g.z, g.w}, uf[4] = {u.x, u.y, u.z, u.w};
+        // gate and up partials of the same slots are fetched together (one L2 round trip per four slots instead of two); each
+        // element is still summed in the order s = 0,1,…
+        const long long ig = r * 2 * inter + gc, iu = ig + up_off;
+        const int cg = partial_count(pi, static_cast<int>(gc)), cu = partial_count(pi, static_cast<int>(gc + up_off));
+        float gf[4] = {0.f, 0.f, 0.f, 0.f}, uf[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s0 = 0; s0 < max(cg, cu); s0 += 4) {
+            float4 pg[4], pu[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (s0 + j < cg) pg[j] = *reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + ig);
+                if (s0 + j < cu) pu[j] = *reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + iu);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (s0 + j < cg) { gf[0] += pg[j].x; gf[1] += pg[j].y; gf[2] += pg[j].z; gf[3] += pg[j].w; }
+                if (s0 + j < cu) { uf[0] += pu[j].x; uf[1] += pu[j].y; uf[2] += pu[j].z; uf[3] += pu[j].w; }
+            }
+        }
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -122,14 +137,44 @@ __device__ __forceinline__ void reduce_rope_kv_warp(const PartialInfo& pi, bf16*
     for (int i = lane * 2; i < half; i += 64) {
         const float c0 = cs[i], c1 = cs[i + 1], s0 = sn[i], s1 = sn[i + 1];
         float qa0, qa1, qb0, qb1, ka0, ka1, kb0, kb1;
-        r2(rowbase + i, qa0, qa1, cnt_q);
-        r2(rowbase + i + half, qb0, qb1, cnt_q);
-        r2(rowbase + hidden + i, ka0, ka1, cnt_k);
-        r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int vi = 2 * i;                                   // lane·4: this lane's four v columns of the same pass
         const bool has_v = vi < head_dim;
-        if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
+        if (uniform) {
+            // the five reductions of this lane (q lo/hi, k lo/hi, v) share ONE slot loop: four slots × five loads in flight per
+            // round trip instead of five loops one after the other (this kernel is pure L2 latency); per element the order is
+            // still s = 0,1,…
+            const int cnt_v = has_v ? partial_count(pi, col_q + 2 * hidden) : 0;
+            const long long oq = rowbase + i, ok = rowbase + hidden + i, ov = rowbase + 2 * hidden + vi;
+            float xq[4] = {0.f, 0.f, 0.f, 0.f}, xk[4] = {0.f, 0.f, 0.f, 0.f};      // {lo.x, lo.y, hi.x, hi.y}
+            for (int sp = 0; sp < max(max(cnt_q, cnt_k), cnt_v); sp += 4) {
+                float2 pq[4][2], pk[4][2];
+                float4 pv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* Ps = P + (sp + j) * stride;
+                    if (sp + j < cnt_q) { pq[j][0] = *reinterpret_cast<const float2*>(Ps + oq); pq[j][1] = *reinterpret_cast<const float2*>(Ps + oq + half); }
+                    if (sp + j < cnt_k) { pk[j][0] = *reinterpret_cast<const float2*>(Ps + ok); pk[j][1] = *reinterpret_cast<const float2*>(Ps + ok + half); }
+                    if (sp + j < cnt_v) pv[j] = *reinterpret_cast<const float4*>(Ps + ov);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sp + j < cnt_q) { xq[0] += pq[j][0].x; xq[1] += pq[j][0].y; xq[2] += pq[j][1].x; xq[3] += pq[j][1].y; }
+                    if (sp + j < cnt_k) { xk[0] += pk[j][0].x; xk[1] += pk[j][0].y; xk[2] += pk[j][1].x; xk[3] += pk[j][1].y; }
+                    if (sp + j < cnt_v) { v.x += pv[j].x; v.y += pv[j].y; v.z += pv[j].z; v.w += pv[j].w; }
+                }
+            }
+            qa0 = __bfloat162float(__float2bfloat16_rn(xq[0])); qa1 = __bfloat162float(__float2bfloat16_rn(xq[1]));
+            qb0 = __bfloat162float(__float2bfloat16_rn(xq[2])); qb1 = __bfloat162float(__float2bfloat16_rn(xq[3]));
+            ka0 = __bfloat162float(__float2bfloat16_rn(xk[0])); ka1 = __bfloat162float(__float2bfloat16_rn(xk[1]));
+            kb0 = __bfloat162float(__float2bfloat16_rn(xk[2])); kb1 = __bfloat162float(__float2bfloat16_rn(xk[3]));
+        } else {
+            r2(rowbase + i, qa0, qa1, cnt_q);
+            r2(rowbase + i + half, qb0, qb1, cnt_q);
+            r2(rowbase + hidden + i, ka0, ka1, cnt_k);
+            r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
+            if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
+        }
         *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(qa0 * c0 - qb0 * s0, qa1 * c1 - qb1 * s1);
         *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(qb0 * c0 + qa0 * s0, qb1 * c1 + qa1 * s1);
         *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(ka0 * c0 - kb0 * s0, ka1 * c1 - kb1 * s1);

@@ -101,7 +101,7 @@ class TeoModel:
         L.check(self.lib.teo_set_pdl(self._h, 1 if enabled else 0), "teo_set_pdl")
 
     def set_decode_chain(self, enabled: bool):
-        """Persistent decode chain kernel (default on) vs one kernel per GEMM; results are bit-identical.  Cached decode graphs
+        """Persistent decode chain kernel vs one kernel per GEMM (the default); results are bit-identical.  Cached decode graphs
         were captured with the previous setting, so they are dropped."""
         L.check(self.lib.teo_set_decode_chain(self._h, 1 if enabled else 0), "teo_set_decode_chain")
         self._decode_states.clear()
