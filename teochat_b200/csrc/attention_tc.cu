@@ -10,8 +10,7 @@
 //   warp 1        MMA issuer (one thread): S_t = Q_t·Kᵀ (both operands K-major in shared memory) into TMEM,
 //                 O_t += P_t·V with P_t read from TMEM (A operand) and V MN-major straight from its TMA tile
 //   warp 2        TMEM allocator (S0 | S1 | O0 | O1; P_t overlays the first half of S_t)
-//   warps 2, 3    q_offset = 1 only: row 0 of the sequence (the ViT CLS query) with mma.sync from the same K/V tiles — the two
-//                 warps take alternate 32-key slices of every block, each with its own online-softmax state, merged at item end
+//   warp 3        q_offset = 1 only: row 0 of the sequence (the ViT CLS query) on CUDA cores from the same K/V tiles
 //   warps 4-7     softmax of tile 0, one thread per query row (= TMEM lane): row max, lazy rescale of O
 //   warps 8-11    softmax of tile 1        (only when the running max grows by > 2^8), exp2, bf16 P → TMEM
 // The two tiles ping-pong: while one tile's rows are in softmax, the tensor core runs the other tile's
@@ -48,7 +47,7 @@ struct FaCfg {
     static constexpr int Q_SETS = 1;
     static constexpr int STAGES = HD == 128 ? 2 : 3;
     static constexpr int TMEM_COLS = (2 * BN + 2 * HD <= 256) ? 256 : 512;
-    static constexpr int SMEM = Q_SETS * Q_SET + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/ + 2 * (HD + 2) * 4 /*row-0 merge*/;
+    static constexpr int SMEM = Q_SETS * Q_SET + 2 * STAGES * KV_TILE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct FaArgs {
@@ -129,7 +128,6 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     uint64_t* p_full = s_full + 2;                              // [2] P_t(j) in TMEM, O_t rescaled (softmax → MMA)
     uint64_t* o_full = p_full + 2;                              // [2] last P·V of tile t complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-    float* row0_merge = reinterpret_cast<float*>(bars + 32);    // [2 item parities][HD + 2]: warp 2's partial state of row 0
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -144,9 +142,9 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&k_full[s], 1);
-            mbar_init(&k_empty[s], 1 + 2 * g.q_offset);       // MMA commit (+ the two row-0 warps)
+            mbar_init(&k_empty[s], 1 + g.q_offset);           // MMA commit (+ the row-0 warp)
             mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1 + 2 * g.q_offset);
+            mbar_init(&v_empty[s], 1 + g.q_offset);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&s_full[t], 1);
@@ -268,20 +266,18 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if ((warp == 2 || warp == 3) && g.q_offset == 1) {
-        // ------------------------------------------------------------------ row 0 of every sequence (two warps, mma.sync)
-        // 16-row flash-attention warps whose only live row is the sequence's row 0: they walk the same K/V ring as the
+    } else if (warp == 3 && g.q_offset == 1) {
+        // ------------------------------------------------------------------ row 0 of every sequence (one warp, mma.sync)
+        // A 16-row flash-attention warp whose only live row is the sequence's row 0: walks the same K/V ring as the
         // MMA warp, 32 keys at a time — q·kᵀ and p·v on mma.sync m16n8k16 with ldmatrix straight from the 128-byte-
-        // swizzled TMA tiles, online softmax in registers, ~130 instructions per 32 keys.  A single warp doing all of a
-        // block was slower than the tensor-core pipeline it shares the ring with (it gated the release of every stage: the
-        // 257th token cost 100 of 275 µs per ViT layer); warp 2 (idle after the TMEM allocation) and warp 3 now take
-        // alternate 32-key slices and merge their (max, sum, O) states through shared memory at the end of the item.
-        // Every block of every item is acknowledged on k_empty / v_empty by BOTH warps (count 3), also for items whose
-        // row 0 belongs to another item (m0 > 0), so that the barrier phases stay in step.
+        // swizzled TMA tiles, online softmax in registers.  ~130 instructions per 32 keys, far off the critical path.
+        // Every block of every item is acknowledged on k_empty / v_empty (count 2), also for items whose row 0
+        // belongs to another item (m0 > 0), so that the barrier phases stay in step.
+        // (Round 2: splitting the row over warps 2 and 3 — alternate 32-key slices, states merged through shared memory — was
+        // built and measured: 284.9 vs 282.7 µs per ViT layer, no gain, reverted; this warp is not what the 257th token costs.)
         constexpr int KS = HD / 16, DT = HD / 8;
         const int gq = lane >> 2, tq = lane & 3;
-        const int half_id = warp - 2;                            // which 32-key slices of a block this warp owns
-        uint32_t kv_cnt = 0, n_mine = 0;
+        uint32_t kv_cnt = 0;
         for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
             const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
             if (!it.valid) continue;
@@ -311,7 +307,7 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                 if (mine) {
                     const uint8_t* sKb = sK + st * KV_TILE;
                     const uint8_t* sVb = sV + st * KV_TILE;
-                    for (int sub = half_id; sub * 32 < n_valid; sub += 2) {
+                    for (int sub = 0; sub * 32 < n_valid; ++sub) {
                         // ---- S[0, 32 keys] = q · Kᵀ
                         float sc[4][4];
 #pragma unroll
@@ -381,29 +377,11 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                     mbar_arrive(&v_empty[st]);
                 }
             }
-            if (mine) {
-                // merge the two warps' states (warp 2 → shared memory → warp 3), fixed order: slices of warp 2 first
-                float* mg = row0_merge + (n_mine & 1) * (HD + 2);
-                if (half_id == 0 && gq == 0) {
-                    if (tq == 0) { mg[HD] = m_run; mg[HD + 1] = l_run; }
+            if (mine && gq == 0) {
+                const float inv = 1.0f / l_run;
+                bf16* op = g.O + static_cast<long long>(it.seq_start) * g.ldo + it.head * HD + 2 * tq;
 #pragma unroll
-                    for (int dt = 0; dt < DT; ++dt) { mg[dt * 8 + 2 * tq] = o[dt][0]; mg[dt * 8 + 2 * tq + 1] = o[dt][1]; }
-                }
-                asm volatile("bar.sync 2, 64;" ::: "memory");
-                if (half_id == 1 && gq == 0) {
-                    const float m0 = mg[HD], l0 = mg[HD + 1];
-                    const float m_new = fmaxf(m0, m_run);                 // warp 2 always owns key 0: m0 is finite
-                    const float a0 = ex2_approx((m0 - m_new) * g.scale_log2);
-                    const float a1 = (m_run == -INFINITY) ? 0.f : ex2_approx((m_run - m_new) * g.scale_log2);
-                    const float inv = 1.0f / (l0 * a0 + l_run * a1);
-                    bf16* op = g.O + static_cast<long long>(it.seq_start) * g.ldo + it.head * HD + 2 * tq;
-#pragma unroll
-                    for (int dt = 0; dt < DT; ++dt) {
-                        const float x0 = mg[dt * 8 + 2 * tq] * a0 + o[dt][0] * a1, x1 = mg[dt * 8 + 2 * tq + 1] * a0 + o[dt][1] * a1;
-                        *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16x2(x0 * inv, x1 * inv);
-                    }
-                }
-                ++n_mine;          // the merge buffer alternates per item: the next item's writes cannot overtake this item's reads
+                for (int dt = 0; dt < DT; ++dt) *reinterpret_cast<uint32_t*>(op + dt * 8) = pack_bf16x2(o[dt][0] * inv, o[dt][1] * inv);
             }
         }
     } else if (warp >= 4) {

@@ -1,7 +1,9 @@
 // Reductions of the decode GEMMs' fp32 stream-K partials fused with the next element-wise stage (SwiGLU, RoPE + KV-page write,
 // residual + RMSNorm, logits), as __device__ functions: the stand-alone glue kernels of kernels_misc.cu and the persistent
 // decode chain kernel (decode_chain.cu) run the SAME code, so both decode paths produce bit-identical results.
-// Fixed summation order s = 0,1,… over the partial slots everywhere (deterministic).
+// Fixed summation order s = 0,1,… over the partial slots everywhere (deterministic).  Partials are read with ld.global.cg (L2 only):
+// inside the chain kernel they were written by OTHER SMs during the same launch, and a line left in this SM's L1 by an earlier
+// launch over the same workspace must not be served instead.
 #pragma once
 #include "common.h"
 #include "ptx.cuh"
@@ -17,28 +19,28 @@ __device__ __forceinline__ float sum_partials_n(const float* __restrict__ P, lon
     float acc = 0.f;
     int s = 0;
     for (; s + 4 <= splits; s += 4) {
-        const float p0 = P[(s + 0) * stride + idx], p1 = P[(s + 1) * stride + idx];
-        const float p2 = P[(s + 2) * stride + idx], p3 = P[(s + 3) * stride + idx];
+        const float p0 = __ldcg(P + (s + 0) * stride + idx), p1 = __ldcg(P + (s + 1) * stride + idx);
+        const float p2 = __ldcg(P + (s + 2) * stride + idx), p3 = __ldcg(P + (s + 3) * stride + idx);
         acc += p0; acc += p1; acc += p2; acc += p3;
     }
-    for (; s < splits; ++s) acc += P[s * stride + idx];
+    for (; s < splits; ++s) acc += __ldcg(P + s * stride + idx);
     return acc;
 }
 __device__ __forceinline__ float4 sum_partials4_n(const float* __restrict__ P, long long stride, int splits, long long idx) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
     for (; s + 4 <= splits; s += 4) {
-        const float4 p0 = *reinterpret_cast<const float4*>(P + (s + 0) * stride + idx);
-        const float4 p1 = *reinterpret_cast<const float4*>(P + (s + 1) * stride + idx);
-        const float4 p2 = *reinterpret_cast<const float4*>(P + (s + 2) * stride + idx);
-        const float4 p3 = *reinterpret_cast<const float4*>(P + (s + 3) * stride + idx);
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(P + (s + 0) * stride + idx));
+        const float4 p1 = __ldcg(reinterpret_cast<const float4*>(P + (s + 1) * stride + idx));
+        const float4 p2 = __ldcg(reinterpret_cast<const float4*>(P + (s + 2) * stride + idx));
+        const float4 p3 = __ldcg(reinterpret_cast<const float4*>(P + (s + 3) * stride + idx));
         acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
         acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
         acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
         acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
     }
     for (; s < splits; ++s) {
-        const float4 p = *reinterpret_cast<const float4*>(P + s * stride + idx);
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(P + s * stride + idx));
         acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
     return acc;
@@ -70,8 +72,8 @@ __device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* 
             float4 pg[4], pu[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (s0 + j < cg) pg[j] = *reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + ig);
-                if (s0 + j < cu) pu[j] = *reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + iu);
+                if (s0 + j < cg) pg[j] = __ldcg(reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + ig));
+                if (s0 + j < cu) pu[j] = __ldcg(reinterpret_cast<const float4*>(pi.P + (s0 + j) * pi.stride + iu));
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -119,14 +121,14 @@ __device__ __forceinline__ void reduce_rope_kv_warp(const PartialInfo& pi, bf16*
         const int splits = uniform ? cnt_hint : partial_count(pi, static_cast<int>(off - row0));
         int sp = 0;
         for (; sp + 4 <= splits; sp += 4) {
-            const float2 p0 = *reinterpret_cast<const float2*>(P + (sp + 0) * stride + off);
-            const float2 p1 = *reinterpret_cast<const float2*>(P + (sp + 1) * stride + off);
-            const float2 p2 = *reinterpret_cast<const float2*>(P + (sp + 2) * stride + off);
-            const float2 p3 = *reinterpret_cast<const float2*>(P + (sp + 3) * stride + off);
+            const float2 p0 = __ldcg(reinterpret_cast<const float2*>(P + (sp + 0) * stride + off));
+            const float2 p1 = __ldcg(reinterpret_cast<const float2*>(P + (sp + 1) * stride + off));
+            const float2 p2 = __ldcg(reinterpret_cast<const float2*>(P + (sp + 2) * stride + off));
+            const float2 p3 = __ldcg(reinterpret_cast<const float2*>(P + (sp + 3) * stride + off));
             x0 += p0.x; x1 += p0.y; x0 += p1.x; x1 += p1.y; x0 += p2.x; x1 += p2.y; x0 += p3.x; x1 += p3.y;
         }
         for (; sp < splits; ++sp) {
-            const float2 p = *reinterpret_cast<const float2*>(P + sp * stride + off);
+            const float2 p = __ldcg(reinterpret_cast<const float2*>(P + sp * stride + off));
             x0 += p.x; x1 += p.y;
         }
         a = __bfloat162float(__float2bfloat16_rn(x0));
@@ -153,9 +155,9 @@ __device__ __forceinline__ void reduce_rope_kv_warp(const PartialInfo& pi, bf16*
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float* Ps = P + (sp + j) * stride;
-                    if (sp + j < cnt_q) { pq[j][0] = *reinterpret_cast<const float2*>(Ps + oq); pq[j][1] = *reinterpret_cast<const float2*>(Ps + oq + half); }
-                    if (sp + j < cnt_k) { pk[j][0] = *reinterpret_cast<const float2*>(Ps + ok); pk[j][1] = *reinterpret_cast<const float2*>(Ps + ok + half); }
-                    if (sp + j < cnt_v) pv[j] = *reinterpret_cast<const float4*>(Ps + ov);
+                    if (sp + j < cnt_q) { pq[j][0] = __ldcg(reinterpret_cast<const float2*>(Ps + oq)); pq[j][1] = __ldcg(reinterpret_cast<const float2*>(Ps + oq + half)); }
+                    if (sp + j < cnt_k) { pk[j][0] = __ldcg(reinterpret_cast<const float2*>(Ps + ok)); pk[j][1] = __ldcg(reinterpret_cast<const float2*>(Ps + ok + half)); }
+                    if (sp + j < cnt_v) pv[j] = __ldcg(reinterpret_cast<const float4*>(Ps + ov));
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -226,7 +228,7 @@ __device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& p
             for (int v = 0; v < MAXV; ++v) {
                 if (s < cnt[vw][v]) {                    // same order s = 0,1,… per element as sum_partials4_n
                     const int c = (v * VT + vw * 32 + lane) * 4;
-                    const float4 p = *reinterpret_cast<const float4*>(pi.P + s * pi.stride + base + c);
+                    const float4 p = __ldcg(reinterpret_cast<const float4*>(pi.P + s * pi.stride + base + c));
                     vals[vw][v][0] += p.x; vals[vw][v][1] += p.y; vals[vw][v][2] += p.z; vals[vw][v][3] += p.w;
                 }
             }
@@ -288,7 +290,7 @@ __device__ __forceinline__ void reduce_logits_part(const PartialInfo& pi, float*
         const int c = static_cast<int>(i % cols);
         const int n = partial_count(pi, c);
         float acc = 0.f;
-        for (int s = 0; s < n; ++s) acc += pi.P[s * pi.stride + i];
+        for (int s = 0; s < n; ++s) acc += __ldcg(pi.P + s * pi.stride + i);
         out[i] = acc;
     }
 }

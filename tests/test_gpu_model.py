@@ -477,8 +477,14 @@ def test_decode_chain_bit_identical_to_kernel_per_gemm(case):
     ids_k, lg_k = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1, return_logits=True)
     graph_k = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1)
     launches_k = model.decode_step_launches
+    _, lg_k2 = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1, return_logits=True)
+    model.set_decode_chain(True)
+    _, lg_c2 = model.generate_batch(ids, frames_u8=frames, max_new_tokens=n_new, eos_token_id=-1, return_logits=True)
     model.set_decode_chain(False)
     assert torch.isfinite(lg_c).all()
+    # each path must first reproduce ITSELF run to run (fixed reduction orders everywhere), then the two must agree
+    assert torch.equal(lg_k, lg_k2), f"per-GEMM path not reproducible: max |diff| {(lg_k - lg_k2).abs().max().item():.3e}"
+    assert torch.equal(lg_c, lg_c2), f"chain path not reproducible: max |diff| {(lg_c - lg_c2).abs().max().item():.3e}"
     assert torch.equal(lg_c, lg_k), f"max |diff| {(lg_c - lg_k).abs().max().item():.3e}"
     assert ids_c == ids_k == graph_c == graph_k
     print(f"{case}: kernels per decode step {launches_c} (chain) vs {launches_k} (per GEMM)")
