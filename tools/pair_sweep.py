@@ -4,6 +4,7 @@ prefill / ViT shapes of the bench step, through the development hook teo_dbg_pai
 runs first.  Development tool:
     python tools/pair_sweep.py time [prefill|vit]      CUDA-event timing of every configuration
     python tools/pair_sweep.py one gm gn r h [which]    one launch per shape of one configuration (for an ncu metrics pass)
+    python tools/pair_sweep.py cublas [prefill|vit]    this kernel against torch.matmul (cuBLASLt) on the same operands, interleaved
 """
 import ctypes as C
 import os
@@ -26,7 +27,7 @@ CONFIGS = [(16, ALL, 0, 0), (8, ALL, 0, 0), (12, ALL, 0, 0), (24, ALL, 0, 0), (3
 
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "time"
-    which = (sys.argv[2] if mode == "time" and len(sys.argv) > 2 else (sys.argv[6] if mode == "one" and len(sys.argv) > 6 else "prefill"))
+    which = (sys.argv[2] if mode in ("time", "cublas") and len(sys.argv) > 2 else (sys.argv[6] if mode == "one" and len(sys.argv) > 6 else "prefill"))
     lib = L.load()
     raw = C.CDLL(L.lib_path())
     raw.teo_dbg_pair_cfg.argtypes = [C.c_int] * 4
@@ -48,6 +49,33 @@ def main():
         def run():
             L.check(lib.teo_gemm_bf16_wblocked(h, A.data_ptr(), K, Wb.data_ptr(), out.data_ptr(), n_out, M, N, K, None, L.ptr(res),
                                                n_out if res is not None else 0, act, 0, None, 0, st))
+        if mode == "cublas":
+            # the library's rate on the same operands, interleaved with ours (same clocks / power state): torch.matmul → cuBLASLt
+            Wt = W.t()
+            raw.teo_dbg_pair_cfg(0, 0, -1, -1)
+            ours, lib_t = [], []
+            for _ in range(6):
+                run()
+                torch.matmul(A, Wt)
+            torch.cuda.synchronize()
+            for rnd in range(6):
+                for which_one in ((0, 1) if rnd % 2 == 0 else (1, 0)):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        if which_one == 0:
+                            run()
+                        else:
+                            torch.matmul(A, Wt)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    (ours if which_one == 0 else lib_t).append(e0.elapsed_time(e1) / 3 * 1e3)
+            a_us, b_us = statistics.median(ours), statistics.median(lib_t)
+            fl = 2.0 * M * N * K
+            print(f"{which} {name:8s} M={M} N={N:5d} K={K:5d}: gemm_pair_kernel (+ its epilogue: {'SwiGLU' if act == 3 else ('residual' if res is not None else ('quick_gelu' if act == 1 else 'plain'))}) "
+                  f"{a_us:8.1f} us {fl / a_us / 1e6:6.0f} TF/s | cuBLAS plain GEMM {b_us:8.1f} us {fl / b_us / 1e6:6.0f} TF/s | ours/cuBLAS time {a_us / b_us:5.3f}", flush=True)
+            del A, W, Wb, out
+            continue
         if mode != "time":
             raw.teo_dbg_pair_cfg(*cfgs[0])
             torch.cuda.profiler.start()
