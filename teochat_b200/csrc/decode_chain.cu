@@ -321,6 +321,7 @@ decode_chain_kernel(const __grid_constant__ CUtensorMap tw0, const __grid_consta
             }
             // ---- the next phase's input complete, everywhere (the producer warps wait on this counter)
             if (p + 1 < a.n_phases) {
+                asm volatile("fence.proxy.async;" ::: "memory");   // this thread's generic-proxy stores → visible to the TMA (async proxy) reads
                 epi_bar_sync();
                 if (t256 == 0) {
                     chain_stamp(a, p, 5);        // this CTA's part of the reduction done

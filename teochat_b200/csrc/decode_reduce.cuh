@@ -85,7 +85,7 @@ __device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gg = __bfloat162float(__float2bfloat16_rn(gf[j])), uu = __bfloat162float(__float2bfloat16_rn(uf[j]));
-            o[j] = (gg / (1.0f + expf(-gg))) * uu;
+            o[j] = __fmul_rn(__fdiv_rn(gg, __fadd_rn(1.0f, expf(-gg))), uu);
         }
         *reinterpret_cast<uint2*>(act + r * inter + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
     }
@@ -177,10 +177,14 @@ __device__ __forceinline__ void reduce_rope_kv_warp(const PartialInfo& pi, bf16*
             r2(rowbase + hidden + i + half, kb0, kb1, cnt_k);
             if (has_v) v = sum_partials4(pi, rowbase + 2 * hidden + vi, static_cast<int>(rowbase - row0) + 2 * hidden + vi);
         }
-        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(qa0 * c0 - qb0 * s0, qa1 * c1 - qb1 * s1);
-        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(qb0 * c0 + qa0 * s0, qb1 * c1 + qa1 * s1);
-        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(ka0 * c0 - kb0 * s0, ka1 * c1 - kb1 * s1);
-        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(kb0 * c0 + ka0 * s0, kb1 * c1 + ka1 * s1);
+        // explicit mul / add roundings (x·cos ± y·sin as HF computes it: two products, one sum): no FMA contraction, so that
+        // this code gives the same bits in whichever kernel it is inlined (stand-alone glue kernel, chain kernel)
+        auto rot_lo = [](float x, float y, float c, float s) { return __fsub_rn(__fmul_rn(x, c), __fmul_rn(y, s)); };
+        auto rot_hi = [](float x, float y, float c, float s) { return __fadd_rn(__fmul_rn(y, c), __fmul_rn(x, s)); };
+        *reinterpret_cast<uint32_t*>(q + i) = pack_bf16x2(rot_lo(qa0, qb0, c0, s0), rot_lo(qa1, qb1, c1, s1));
+        *reinterpret_cast<uint32_t*>(q + i + half) = pack_bf16x2(rot_hi(qa0, qb0, c0, s0), rot_hi(qa1, qb1, c1, s1));
+        *reinterpret_cast<uint32_t*>(kdst + i) = pack_bf16x2(rot_lo(ka0, kb0, c0, s0), rot_lo(ka1, kb1, c1, s1));
+        *reinterpret_cast<uint32_t*>(kdst + i + half) = pack_bf16x2(rot_hi(ka0, kb0, c0, s0), rot_hi(ka1, kb1, c1, s1));
         if (has_v) *reinterpret_cast<uint2*>(vdst + vi) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
@@ -247,7 +251,7 @@ __device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& p
                 vals[vw][v][2] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][2] + bf16_lo(r.y)));
                 vals[vw][v][3] = __bfloat162float(__float2bfloat16_rn(vals[vw][v][3] + bf16_hi(r.y)));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) sq += vals[vw][v][j] * vals[vw][v][j];
+                for (int j = 0; j < 4; ++j) sq = __fmaf_rn(vals[vw][v][j], vals[vw][v][j], sq);
             }
         }
         parts[vw] = warp_sum(sq);
@@ -263,7 +267,7 @@ __device__ __forceinline__ void reduce_residual_rmsnorm_row(const PartialInfo& p
 #pragma unroll
     for (int r = 0; r < VC; ++r) tot += cta_part[r];
     sync256();                                           // cta_part may be rewritten by the next row
-    const float rstd = 1.0f / sqrtf(tot / static_cast<float>(d) + eps);
+    const float rstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__fdiv_rn(tot, static_cast<float>(d)), eps)));
 #pragma unroll
     for (int vw = 0; vw < 4; ++vw) {
         const int vt = vw * 32 + lane;

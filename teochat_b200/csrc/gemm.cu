@@ -139,7 +139,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) trace_stamp(g, 1);     // barriers, TMEM, descriptors ready
+    if (threadIdx.x == 0 && g.trace) {            // slot 1: the SM this CTA runs on (tools/dec_gemm_skew.py)
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g.trace[blockIdx.x * 8 + 1] = smid;
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer

@@ -403,7 +403,7 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
             vals[v][2] = __bfloat162float(__float2bfloat16_rn(acc.z + bf16_lo(r.y)));
             vals[v][3] = __bfloat162float(__float2bfloat16_rn(acc.w + bf16_hi(r.y)));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sq += vals[v][j] * vals[v][j];
+            for (int j = 0; j < 4; ++j) sq = __fmaf_rn(vals[v][j], vals[v][j], sq);      // explicit: same bits as reduce_residual_rmsnorm_row
         }
     }
     sq = warp_sum(sq);
@@ -420,7 +420,7 @@ reduce_residual_rmsnorm_kernel(PartialInfo pi, bf16* __restrict__ x, const bf16*
 #pragma unroll
     for (int r = 0; r < RN_CLUSTER; ++r) tot += *cluster.map_shared_rank(&cta_part, r);     // fixed order: deterministic
     cluster.sync();                                   // nobody leaves while its shared memory may still be read
-    const float rstd = 1.0f / sqrtf(tot / static_cast<float>(d) + eps);
+    const float rstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__fdiv_rn(tot, static_cast<float>(d)), eps)));
 #pragma unroll
     for (int v = 0; v < RN_MAXV; ++v) {
         const int c = (v * RN_THREADS + threadIdx.x) * 4;

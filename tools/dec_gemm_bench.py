@@ -55,7 +55,7 @@ def main():
         t = t[t[:, 0] > 0]
         t0 = int(t[:, 0].min())
         rel = (t - t0).float() / 1e3
-        names = ["enter", "setup done", "ring filled", "dep wait done", "first operands", "last MMA issued", "epilogue done", "exit"]
+        names = ["enter", "(smid)", "ring filled", "dep wait done", "first operands", "last MMA issued", "epilogue done", "exit"]
         print(f"{name:8s} M={M} N={N} K={K}: GEMM + reduce {us:6.1f} us per call ({ideal:5.1f} us of weight streaming at 6.45 TB/s); "
               f"timeline over {t.shape[0]} CTAs, us from first entry (min / median / max):")
         for j, n in enumerate(names):

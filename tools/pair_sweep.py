@@ -35,7 +35,7 @@ def main():
     L.check(lib.teo_create(0, C.byref(h)))
     st = torch.cuda.current_stream().cuda_stream
     dev = "cuda"
-    cfgs = CONFIGS if mode == "time" else [tuple(int(x) for x in sys.argv[2:6])]
+    cfgs = [tuple(int(x) for x in sys.argv[2:6])] if mode == "one" else CONFIGS
     M, shapes = SHAPES[which]
     for name, N, K, act in shapes:
         A = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
