@@ -85,18 +85,18 @@ struct Scheduler {
     }
 };
 
-template <int BN>
+template <int BN, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs g) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, SK>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;               // 1024-byte aligned (stage sizes are)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -255,7 +255,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            if (g.tma_epi) {
+            if (!SK && g.tma_epi) {             // (the stream-K instantiation has no staging buffer)
                 staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, m_blk, n_blk, stg, rbar, rph, lane, q, hsel, [&] {
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[as]);
@@ -514,17 +514,17 @@ extern "C" size_t teo_gemm_workspace_bytes(int M, int N, int K) {
     return static_cast<size_t>(19) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float);
 }
 
-template <int BN>
+template <int BN, bool SK = false>
 static int launch_cfg(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                       const GemmArgs& g, int units, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, SK>;
     static bool attr_set = false;
     if (!attr_set) {
-        TEO_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TEO_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = std::min(units, h->num_sms);
-    TEO_CUDA(launch_kc(PDL_GEMM, gemm_tn_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tr, g));
+    TEO_CUDA(launch_kc(PDL_GEMM, gemm_tn_kernel<BN, SK>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tr, g));
     TEO_LAUNCH_CHECK("gemm_tn_kernel");
     h->launches++;
     return TEO_OK;
@@ -561,9 +561,9 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     TEO_TRY(get_tmap_bf16(h, A, M, K, lda, p.bn, &tb));
     int rc;
     switch (p.bn) {
-        case 32: rc = launch_cfg<32>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
-        case 64: rc = launch_cfg<64>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
-        default: rc = launch_cfg<128>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
+        case 32: rc = launch_cfg<32, true>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
+        case 64: rc = launch_cfg<64, true>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
+        default: rc = launch_cfg<128, true>(h, ta, tb, ta, ta, g, p.sk_grid, stream); break;
     }
     TEO_TRY(rc);
     info->P = static_cast<const float*>(workspace);
@@ -667,11 +667,19 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
     if (!g.tma_epi) tc = tr = ta;     // unused by the direct-store epilogue
     const int units = p.swap ? p.sk_grid : ((g.M + BM - 1) / BM) * ((g.N + p.bn - 1) / p.bn);
     int rc;
-    switch (p.bn) {
-        case 32: rc = launch_cfg<32>(h, ta, tb, tc, tr, g, units, stream); break;
-        case 64: rc = launch_cfg<64>(h, ta, tb, tc, tr, g, units, stream); break;
-        case 128: rc = launch_cfg<128>(h, ta, tb, tc, tr, g, units, stream); break;
-        default: rc = launch_cfg<256>(h, ta, tb, tc, tr, g, units, stream); break;
+    if (p.swap) {                     // stream-K schedule: deeper ring, no staging buffer
+        switch (p.bn) {
+            case 32: rc = launch_cfg<32, true>(h, ta, tb, tc, tr, g, units, stream); break;
+            case 64: rc = launch_cfg<64, true>(h, ta, tb, tc, tr, g, units, stream); break;
+            default: rc = launch_cfg<128, true>(h, ta, tb, tc, tr, g, units, stream); break;
+        }
+    } else {
+        switch (p.bn) {
+            case 32: rc = launch_cfg<32>(h, ta, tb, tc, tr, g, units, stream); break;
+            case 64: rc = launch_cfg<64>(h, ta, tb, tc, tr, g, units, stream); break;
+            case 128: rc = launch_cfg<128>(h, ta, tb, tc, tr, g, units, stream); break;
+            default: rc = launch_cfg<256>(h, ta, tb, tc, tr, g, units, stream); break;
+        }
     }
     TEO_TRY(rc);
     if (p.swap) {

@@ -43,13 +43,19 @@ struct GemmArgs {
     unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 
-template <int BN>
+// SK = the small-M stream-K schedule (decode): partial outputs go straight from registers to global memory, so the epilogue
+// staging buffer is dropped and its 32 KiB go to the ring — the weight stream is latency-bound (bytes in flight per SM × 148 /
+// HBM latency), measured 5.1 TB/s with 8 stages of 16 KiB weights per SM (profiles/r02_dec_gemm_skew.txt).
+template <int BN, bool SK = false>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+    static constexpr int STAGING = SK ? 0 : STAGING_BYTES;
+    static constexpr int BUDGET = SK ? 229376 : 196608;
+    static constexpr int MAX_STAGES = SK ? 11 : 8;
+    static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
