@@ -52,7 +52,7 @@ class TeoModel:
     """Duck-types what the reference's callers touch on ``model``: ``generate``,
     ``device``, ``config``, ``get_image_tower()``, settable ``model.video_tower``."""
 
-    VIT_CHUNK_FRAMES = 512
+    VIT_CHUNK_FRAMES = int(os.environ.get("TEO_VIT_CHUNK", "512"))     # frames per teo_vit_encode call (workspace ∝ this)
 
     def __init__(self, cfg: TeoConfig, weights: TeoWeights, device=None, precision: Optional[str] = None):
         """``precision``: "bf16" (default; bf16 activations / KV, the measured path) or "exact" — the parity mode of
