@@ -75,6 +75,32 @@ int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* W, int ldw,
                   int K, const void* bias, const void* residual, int ldr, int act, int out_fp32, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* The same GEMM with the full option set.  LayerNorm FOLDED into the linear that consumes it (HF CLIPEncoderLayer:
+ * layer_norm1 -> q/k/v proj, layer_norm2 -> fc1, modeling_image.py:136-151): A holds the UN-normalised rows x [M,K], W the
+ * weights pre-multiplied by the LayerNorm gain, W'[n,k] = bf16(gamma_k * W[n,k]), and
+ *     C[m,n] = act( rstd_m * (sum_k x[m,k] W'[n,k] - mean_m * ln_c[n]) + ln_bias[n] )
+ * with ln_c[n] = sum_k W'[n,k] and ln_bias[n] = sum_k beta_k W[n,k] + b[n] (both f32 [N], 16-byte aligned) — i.e.
+ * act(LayerNorm(x) W^T + b) without the normalised tensor ever reaching HBM.  mean_m / rstd_m come from ln_stats, f32
+ * [M][ln_slots][2] partial (sum x, sum x^2) per row, which the GEMM that PRODUCED x writes when given stats_out (f32
+ * [M][teo_gemm_stats_slots(M,N,K)][2], statistics of the bf16 values it stores), or teo_row_stats computes.  Tiled schedule
+ * only (M > 128), bf16 output, bias == NULL together with ln_stats.  Zero-initialise the struct for plain behaviour. */
+typedef struct {
+    const void* bias;      /* bf16 [N] or NULL */
+    const void* residual;  /* bf16 [M, ldr] or NULL */
+    int ldr, act, out_fp32, w_blocked;
+    const void* ln_stats;  /* f32 [M][ln_slots][2] or NULL */
+    const void* ln_c;      /* f32 [N] */
+    const void* ln_bias;   /* f32 [N] */
+    int ln_slots;
+    float ln_eps;
+    void* stats_out;       /* f32 [M][teo_gemm_stats_slots(M,N,K)][2] or NULL */
+} teo_gemm_opts;
+int teo_gemm_stats_slots(int M, int N, int K);
+int teo_gemm_bf16_ex(teo_handle* h, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                     const teo_gemm_opts* opts, void* workspace, size_t workspace_bytes, void* stream);
+/* stats f32 [rows][slots][2]: slot 0 = (sum x, sum x^2) of the bf16 row x[r, 0..d), the other slots zero */
+int teo_row_stats(const void* x, void* stats, int rows, int d, int slots, void* stream);
+
 /* Blocked weight layout.  A weight matrix W[N,K] (N % 128 == 0, K % 64 == 0) may be stored as
  * bf16 [N/128][K/64][128][64]: each 128-row × 64-column operand tile is 16 KiB CONTIGUOUS in HBM, so the TMA
  * producer streams whole DRAM bursts instead of 128 separate 128-byte row pieces 2·K bytes apart (what bounds the
@@ -238,6 +264,12 @@ typedef struct {
     const void *ln2_w, *ln2_b;   /* [d] */
     const void *fc1_w, *fc1_b;   /* [inter, d], [inter] */
     const void *fc2_w, *fc2_b;   /* [d, inter], [d] */
+    /* optional (all six or none): LayerNorm folded into the two linears that consume it (teo_gemm_bf16_ex):
+     * qkv_wf = bf16(ln1_w * qkv_w) [3d,d], qkv_c = rowsum(qkv_wf) f32 [3d], qkv_bf = qkv_w·ln1_b + qkv_b f32 [3d]; fc1_* likewise
+     * with ln2.  When present (and the batch is large enough for the tiled GEMM) teo_vit_encode runs no LayerNorm kernels:
+     * the out-proj / fc2 GEMMs emit the row statistics of the residual stream they write. */
+    const void *qkv_wf, *qkv_c, *qkv_bf;
+    const void *fc1_wf, *fc1_c, *fc1_bf;
 } teo_vit_layer;
 
 typedef struct {

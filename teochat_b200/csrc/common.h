@@ -128,6 +128,17 @@ struct GemmEpilogue {
     int act = TEO_ACT_NONE;
     int out_fp32 = 0;                 // C is float instead of bf16
     int residual_f32 = 0;             // residual is float [M, ldr] (needs out_fp32; may alias C)
+    // LayerNorm folded into this GEMM (tiled schedule, bf16 output): A holds the UN-normalised rows x, W the weights pre-multiplied
+    // by the LayerNorm gain, W'[n,k] = bf16(γ_k·W[n,k]);  C = act(rstd_m·(x·W'ᵀ − mean_m·ln_c) + ln_bias) with
+    // ln_c[n] = Σ_k W'[n,k], ln_bias[n] = Σ_k β_k·W[n,k] + b[n]  (= LayerNorm(x)·Wᵀ + b up to the rounding of W').
+    // ln_stats: f32 [M][ln_slots][2] partial (Σx, Σx²) per input row, written by the GEMM that produced x (stats_out) or by
+    // teo_row_stats.  `bias` must be null when ln_stats is set.
+    const float* ln_stats = nullptr;
+    const float* ln_c = nullptr;
+    const float* ln_bias = nullptr;
+    int ln_slots = 0;
+    float ln_eps = 0.f;
+    float* stats_out = nullptr;       // f32 [M][teo_gemm_stats_slots(M,N,K)][2]: (Σ, Σ²) partials of the bf16 rows this GEMM writes
     int k_planes = 1;                 // exact mode: A is [M, k_planes·K] — an fp32 activation split into k_planes bf16 terms
                                       // (hi | mid | lo) stored side by side; every plane is multiplied by the same W[N,K]
 };

@@ -603,8 +603,24 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
             return TEO_ERR_UNSUPPORTED;
         }
     }
+    const bool ln_any = ep.ln_stats != nullptr || ep.stats_out != nullptr;
+    if (ln_any) {
+        TEO_CHECK_ARG(!p.swap && !ep.out_fp32 && ep.act != TEO_ACT_SWIGLU_PAIRS,
+                      "gemm: folded LayerNorm / row statistics need the tiled schedule (M > 128 or N < 256) with bf16 output");
+        TEO_CHECK_ARG(ep.ln_stats == nullptr || (ep.ln_c && ep.ln_bias && ep.ln_slots > 0 && ep.bias == nullptr && ep.k_planes == 1 &&
+                                                 (reinterpret_cast<uintptr_t>(ep.ln_c) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.ln_bias) & 15) == 0),
+                      "gemm: folded LayerNorm needs ln_c, ln_bias (16-byte aligned), ln_slots > 0 and no separate bias");
+    }
     GemmArgs g{};
     g.trace = next_trace_slot();
+    g.ln_stats = ep.ln_stats;
+    g.ln_c = ep.ln_c;
+    g.ln_bias = ep.ln_bias;
+    g.ln_slots = ep.ln_slots;
+    g.ln_inv_d = 1.0f / static_cast<float>(Kw);
+    g.ln_eps = ep.ln_eps;
+    g.stats_out = ep.stats_out;
+    g.stats_slots = 2 * ((N + p.bn - 1) / p.bn);
     g.act = ep.act;
     g.out_fp32 = ep.out_fp32;
     g.bias = ep.bias;
@@ -693,6 +709,31 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
         h->launches++;
     }
     return TEO_OK;
+}
+
+extern "C" int teo_gemm_stats_slots(int M, int N, int K) {
+    const GemmPlan p = plan_gemm(M, N, K, 148);
+    return p.swap ? 0 : 2 * ((N + p.bn - 1) / p.bn);
+}
+
+extern "C" int teo_gemm_bf16_ex(teo_handle* h, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                                const teo_gemm_opts* o, void* workspace, size_t workspace_bytes, void* stream) {
+    TEO_CHECK_ARG(A && W && C && o, "gemm_ex: null operand");
+    TEO_CHECK_ARG(o->act >= TEO_ACT_NONE && o->act <= TEO_ACT_SWIGLU_PAIRS, "gemm_ex: unknown activation %d", o->act);
+    GemmEpilogue ep;
+    ep.bias = static_cast<const bf16*>(o->bias);
+    ep.residual = static_cast<const bf16*>(o->residual);
+    ep.ldr = o->ldr;
+    ep.act = o->act;
+    ep.out_fp32 = o->out_fp32;
+    ep.ln_stats = static_cast<const float*>(o->ln_stats);
+    ep.ln_c = static_cast<const float*>(o->ln_c);
+    ep.ln_bias = static_cast<const float*>(o->ln_bias);
+    ep.ln_slots = o->ln_slots;
+    ep.ln_eps = o->ln_eps;
+    ep.stats_out = static_cast<float*>(o->stats_out);
+    return launch_gemm(h, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), o->w_blocked ? K : ldw, C, ldc, M, N, K, ep, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream), o->w_blocked);
 }
 
 extern "C" int teo_gemm_bf16(teo_handle* h, const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M,

@@ -40,6 +40,16 @@ struct GemmArgs {
                                 // activation split into hi | mid | lo bf16 terms, all multiplied by the same weights)
     int residual_f32;           // residual is float (direct-store epilogue only)
     int group_n, raster, l2_hint;   // CTA-pair kernel: supertile width (tile columns), supertile order, L2 eviction hints (gemm_pair.cu)
+    // LayerNorm folded into the GEMM that consumes it (staged epilogue only; see GemmEpilogue in common.h):
+    //   C[m,n] = act( rstd_m · (acc[m,n] − mean_m · ln_c[n]) + ln_bias[n] ),  mean / rstd from the row statistics ln_stats
+    const float* ln_stats;      // f32 [M][ln_slots][2]: partial (Σx, Σx²) of the INPUT rows
+    const float* ln_c;          // f32 [N]: Σ_k W'[n,k]
+    const float* ln_bias;       // f32 [N]: Σ_k β_k·W[n,k] + b[n]
+    int ln_slots;
+    float ln_inv_d, ln_eps;     // 1 / K of the normalised dimension, epsilon
+    // … and the row statistics of the OUTPUT (the residual stream this GEMM writes) for the next folded LayerNorm:
+    float* stats_out;           // f32 [M][stats_slots][2]; slot = 2·(column tile) + (column-chunk parity of the writing warp)
+    int stats_slots;
     unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 
@@ -143,6 +153,16 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
         // ---- staged path: 64-column chunks → swizzled smem → TMA store
         const int row0 = m_blk * BM + q * 32;
         const bool has_res = g.residual != nullptr;
+        // folded LayerNorm: this thread's row statistics (fixed summation order over the producer's slots → deterministic)
+        float ln_mu = 0.f, ln_rstd = 1.f;
+        if (g.ln_stats != nullptr && row0 + lane < g.M) {
+            const float* st = g.ln_stats + static_cast<long long>(row0 + lane) * g.ln_slots * 2;
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < g.ln_slots; ++i) { s1 += st[2 * i]; s2 += st[2 * i + 1]; }
+            ln_mu = s1 * g.ln_inv_d;
+            ln_rstd = rsqrtf(fmaxf(s2 * g.ln_inv_d - ln_mu * ln_mu, 0.f) + g.ln_eps);
+        }
+        float st1 = 0.f, st2 = 0.f;            // Σ, Σ² of the bf16 values this warp writes for its row
 #pragma unroll 1
         for (int cj = hsel; cj < BN / 64; cj += 2) {
             const int n0 = n_blk * BN + cj * 64;
@@ -172,7 +192,14 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
                 const int n = n0 + c * 8;
-                if (g.bias && n < g.N) {
+                if (g.ln_stats != nullptr && n < g.N) {
+                    const float4 c0 = *reinterpret_cast<const float4*>(g.ln_c + n), c1 = *reinterpret_cast<const float4*>(g.ln_c + n + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(g.ln_bias + n), b1 = *reinterpret_cast<const float4*>(g.ln_bias + n + 4);
+                    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = fmaf(ln_rstd, x[j] - ln_mu * cc[j], bb[j]);
+                } else if (g.bias && n < g.N) {
                     const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n);
                     const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
@@ -189,8 +216,18 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
                 }
-                *slot = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                   pack_bf16x2(x[6], x[7]));
+                const uint4 packed = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                                pack_bf16x2(x[6], x[7]));
+                *slot = packed;
+                if (g.stats_out != nullptr) {          // statistics of the values AS STORED (bf16), columns past N hold zeros
+                    const uint32_t pw[4] = {packed.x, packed.y, packed.z, packed.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float lo = bf16_lo(pw[j]), hi = bf16_hi(pw[j]);
+                        st1 += lo + hi;
+                        st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
+                    }
+                }
             }
             fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
             __syncwarp();
@@ -201,6 +238,11 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
         }
         if (hsel >= BN / 64 || n_blk * BN + hsel * 64 >= g.N) {   // this warp owned no chunk of the tile
             release();
+        }
+        if (g.stats_out != nullptr && row0 + lane < g.M) {         // (zeros from a warp that owned no chunk: the consumer sums all slots)
+            float* so = g.stats_out + (static_cast<long long>(row0 + lane) * g.stats_slots + n_blk * 2 + hsel) * 2;
+            so[0] = st1;
+            so[1] = st2;
         }
     }
 }

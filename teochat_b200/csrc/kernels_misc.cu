@@ -219,6 +219,25 @@ static int launch_norm(const bf16* in, const bf16* w, const bf16* b, bf16* out, 
     return TEO_OK;
 }
 
+// (Σx, Σx²) of every bf16 row into slot 0 of stats[row][slots][2] (other slots zero): the row statistics a folded LayerNorm
+// (gemm_common.cuh) reads, for rows that no GEMM epilogue produced.  One warp per row.
+__global__ void row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int rows, int d, int slots) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const bf16* src = x + static_cast<size_t>(row) * d;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+        float v[8];
+        load8(src + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    float* so = stats + static_cast<size_t>(row) * slots * 2;
+    for (int i = lane; i < 2 * slots; i += 32) so[i] = i == 0 ? s1 : (i == 1 ? s2 : 0.f);
+}
+
 // ------------------------------------------------------------------------------ small copies / elementwise
 __global__ void drop_cls_kernel(const uint4* __restrict__ hidden, uint4* __restrict__ feats, int n_patches, int d8, size_t total) {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -672,6 +691,13 @@ extern "C" int teo_vit_assemble_preln(const void* patch_out, const void* cls, co
     return launch_norm<1>(static_cast<const bf16*>(patch_out), static_cast<const bf16*>(ln_w), static_cast<const bf16*>(ln_b),
                           static_cast<bf16*>(hidden), n_frames * (n_patches + 1), d, eps, static_cast<const bf16*>(cls),
                           static_cast<const bf16*>(pos), n_patches, static_cast<cudaStream_t>(stream));
+}
+extern "C" int teo_row_stats(const void* x, void* stats, int rows, int d, int slots, void* stream) {
+    TEO_CHECK_ARG(x && stats && rows > 0 && d > 0 && d % 8 == 0 && slots > 0, "row_stats: bad arguments (rows=%d d=%d slots=%d)", rows, d, slots);
+    row_stats_kernel<<<(rows * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), static_cast<float*>(stats),
+                                                                                             rows, d, slots);
+    TEO_LAUNCH_CHECK("row_stats_kernel");
+    return TEO_OK;
 }
 extern "C" int teo_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int d, float eps, void* stream) {
     TEO_CHECK_ARG(x && w && b && y, "layernorm: null pointer");

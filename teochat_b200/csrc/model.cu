@@ -88,7 +88,7 @@ using namespace teo;
 
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" const char* teo_last_error(void) { return g_err; }
-extern "C" int teo_abi_version(void) { return 3; }
+extern "C" int teo_abi_version(void) { return 4; }
 #ifndef TEO_BUILD_DIGEST
 #define TEO_BUILD_DIGEST "unknown"
 #endif
@@ -155,8 +155,11 @@ static size_t vit_gemm_ws_bytes(const teo_vit_model* m, int n) {
     return b;
 }
 
+extern "C" int teo_gemm_stats_slots(int M, int N, int K);
+extern "C" int teo_row_stats(const void* x, void* stats, int rows, int d, int slots, void* stream);
+
 static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patches, bf16** patch_out, bf16** hidden, bf16** ln_out,
-                            bf16** qkv, bf16** attn, bf16** mlp, int** cu, uint8_t** gemm_ws = nullptr) {
+                            bf16** qkv, bf16** attn, bf16** mlp, int** cu, uint8_t** gemm_ws = nullptr, float** stats = nullptr) {
     const int g = m->image / m->patch, np = g * g;
     const size_t rows = static_cast<size_t>(n) * (np + 1);
     Arena local(nullptr, 0);
@@ -171,6 +174,8 @@ static size_t vit_ws_layout(const teo_vit_model* m, int n, Arena* a, bf16** patc
     p = A.take<bf16>(rows * m->inter); if (mlp) *mlp = p;
     int* c = A.take<int>(n + 1); if (cu) *cu = c;
     uint8_t* gw = A.take<uint8_t>(vit_gemm_ws_bytes(m, n)); if (gemm_ws) *gemm_ws = gw;   // small batches run the small-M GEMM schedule
+    float* st = A.take<float>(rows * 2 * std::max(1, teo_gemm_stats_slots(static_cast<int>(rows), m->hidden, m->hidden)));   // folded-LayerNorm row statistics
+    if (stats) *stats = st;
     return A.off;
 }
 
@@ -194,7 +199,8 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     bf16 *patches, *patch_out, *hidden, *ln_out, *qkv, *attn, *mlp;
     int* cu;
     uint8_t* gws;
-    vit_ws_layout(m, n_frames, &A, &patches, &patch_out, &hidden, &ln_out, &qkv, &attn, &mlp, &cu, &gws);
+    float* stats;
+    vit_ws_layout(m, n_frames, &A, &patches, &patch_out, &hidden, &ln_out, &qkv, &attn, &mlp, &cu, &gws, &stats);
     const size_t gws_bytes = vit_gemm_ws_bytes(m, n_frames);
     if (!A.ok) {
         set_error("vit_encode: workspace too small (%zu needed, %zu given)", A.off, workspace_bytes);
@@ -210,8 +216,46 @@ extern "C" int teo_vit_encode(teo_handle* h, const teo_vit_model* m, const void*
     TEO_LAUNCH_CHECK("fill_cu_seqlens_kernel");
     h->launches += 3;
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    // LayerNorm folded into the q/k/v and fc1 linears (teo_gemm_bf16_ex): no LayerNorm kernels, the normalised tensor never reaches HBM;
+    // the out-proj / fc2 GEMMs emit the row statistics of the residual stream they write.  Needs the tiled GEMM schedule (rows > 128).
+    const int st_slots = teo_gemm_stats_slots(rows, d, d);
+    bool folded = rows > 128 && st_slots > 0 && m->layers_run > 0;
+    for (int l = 0; l < m->layers_run && folded; ++l) {
+        const teo_vit_layer& L = m->layers[l];
+        folded = L.qkv_wf && L.qkv_c && L.qkv_bf && L.fc1_wf && L.fc1_c && L.fc1_bf;
+    }
+    if (folded) {
+        TEO_TRY(teo_row_stats(hidden, stats, rows, d, st_slots, stream));
+        h->launches += 1;
+    }
     for (int l = 0; l < m->layers_run; ++l) {
         const teo_vit_layer& L = m->layers[l];
+        if (folded) {
+            GemmEpilogue e1;
+            e1.ln_stats = stats; e1.ln_slots = st_slots; e1.ln_eps = m->eps;
+            e1.ln_c = static_cast<const float*>(L.qkv_c); e1.ln_bias = static_cast<const float*>(L.qkv_bf);
+            TEO_TRY(launch_gemm(h, hidden, d, static_cast<const bf16*>(L.qkv_wf), d, qkv, 3 * d, rows, 3 * d, d, e1, gws, gws_bytes, stream, m->w_blocked));
+            TEO_TRY(launch_flash_attention_tc(h, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu, n_frames, np + 1, rows, m->heads, hd,
+                                              scale, 0, (np % 128 == 0 && flash_use_tc() && (hd == 64 || hd == 128)) ? 1 : 0, stream));
+            GemmEpilogue e2;
+            e2.bias = static_cast<const bf16*>(L.out_b);
+            e2.residual = hidden; e2.ldr = d;
+            e2.stats_out = stats;
+            TEO_TRY(launch_gemm(h, attn, d, static_cast<const bf16*>(L.out_w), d, hidden, d, rows, d, d, e2, gws, gws_bytes, stream, m->w_blocked));
+            GemmEpilogue e3;
+            e3.ln_stats = stats; e3.ln_slots = st_slots; e3.ln_eps = m->eps;
+            e3.ln_c = static_cast<const float*>(L.fc1_c); e3.ln_bias = static_cast<const float*>(L.fc1_bf);
+            e3.act = m->act;
+            TEO_TRY(launch_gemm(h, hidden, d, static_cast<const bf16*>(L.fc1_wf), d, mlp, m->inter, rows, m->inter, d, e3, gws, gws_bytes, stream, m->w_blocked));
+            GemmEpilogue e4;
+            e4.bias = static_cast<const bf16*>(L.fc2_b);
+            e4.residual = hidden; e4.ldr = d;
+            e4.stats_out = stats;
+            TEO_TRY(launch_gemm(h, mlp, m->inter, static_cast<const bf16*>(L.fc2_w), m->inter, hidden, d, rows, d, m->inter, e4, gws, gws_bytes,
+                                stream, m->w_blocked));
+            h->launches += 1;
+            continue;
+        }
         TEO_TRY(teo_layernorm(hidden, L.ln1_w, L.ln1_b, ln_out, rows, d, m->eps, stream));
         GemmEpilogue e1;
         e1.bias = static_cast<const bf16*>(L.qkv_b);

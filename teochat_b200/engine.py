@@ -131,9 +131,11 @@ class TeoModel:
         p = lambda k: t[k].data_ptr()
         n_run = cfg.vit_layers_run
         self._vit_layers = (L.VitLayer * max(n_run, 1))()
+        fold = (not self.exact) and getattr(self.w, "ln_folded", False) and os.environ.get("TEO_VIT_LN_FOLD", "1") != "0"
         for i in range(n_run):
             for f, _ in L.VitLayer._fields_:
-                setattr(self._vit_layers[i], f, p(f"vit.{i}.{f}"))
+                folded_field = f.endswith(("_wf", "_c", "_bf"))
+                setattr(self._vit_layers[i], f, (p(f"vit.{i}.{f}") if fold else None) if folded_field else p(f"vit.{i}.{f}"))
         self._vit = L.VitModel(hidden=v.hidden_size, inter=v.intermediate_size, heads=v.num_attention_heads,
                                image=v.image_size, patch=v.patch_size, kpad=self.w.kpad,
                                act=L.ACT_BY_NAME[v.hidden_act], layers_run=n_run, eps=v.layer_norm_eps,

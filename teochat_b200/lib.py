@@ -22,9 +22,14 @@ class TeoError(RuntimeError):
     pass
 
 
+class GemmOpts(C.Structure):
+    _fields_ = [("bias", vp), ("residual", vp), ("ldr", C.c_int), ("act", C.c_int), ("out_fp32", C.c_int), ("w_blocked", C.c_int),
+                ("ln_stats", vp), ("ln_c", vp), ("ln_bias", vp), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("stats_out", vp)]
+
+
 class VitLayer(C.Structure):
     _fields_ = [(n, vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b",
-                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+                                  "fc1_w", "fc1_b", "fc2_w", "fc2_b", "qkv_wf", "qkv_c", "qkv_bf", "fc1_wf", "fc1_c", "fc1_bf")]
 
 
 class VitModel(C.Structure):
@@ -64,6 +69,9 @@ _SIGS = {
     "teo_init_u8_hash": (i, [vp, sz, u64, vp]),
     "teo_gemm_workspace_bytes": (sz, [i, i, i]),
     "teo_gemm_bf16": (i, [vp, vp, i, vp, i, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]),
+    "teo_gemm_stats_slots": (i, [i, i, i]),
+    "teo_gemm_bf16_ex": (i, [vp, vp, i, vp, i, vp, i, i, i, i, C.POINTER(GemmOpts), vp, sz, vp]),
+    "teo_row_stats": (i, [vp, vp, i, i, i, vp]),
     "teo_gemm_bf16_wblocked": (i, [vp, vp, i, vp, vp, i, i, i, i, vp, vp, i, i, i, vp, sz, vp]),
     "teo_weight_to_blocked": (i, [vp, vp, i, i, vp]),
     "teo_patchify_u8_nhwc": (i, [vp, vp, i, i, i, i, vp]),

@@ -135,6 +135,7 @@ class TeoWeights:
         self.t = t
         self.blocked: Dict[str, bool] = {}
         self.gate_up_interleaved = False
+        self.ln_folded = False
 
     # HF name → destination view (contiguous row slice of a fused buffer), or None for patch_w
     def _dest(self, name: str) -> Optional[torch.Tensor]:
@@ -224,7 +225,8 @@ class TeoWeights:
     # ---- blocked GEMM-weight layout (include/teochat_b200.h: teo_weight_to_blocked) -----------------------
     def _gemm_weight_groups(self):
         v, l = self.cfg.vision, self.cfg.llama
-        vit = ["vit.patch_w"] + [f"vit.{i}.{n}" for i in range(v.num_hidden_layers) for n in ("qkv_w", "out_w", "fc1_w", "fc2_w")]
+        folded = ("qkv_wf", "fc1_wf") if self.ln_folded else ()
+        vit = ["vit.patch_w"] + [f"vit.{i}.{n}" for i in range(v.num_hidden_layers) for n in ("qkv_w", "out_w", "fc1_w", "fc2_w") + folded]
         proj = ["proj.w0", "proj.w2"]
         llama = [f"llama.{i}.{n}" for i in range(l.num_hidden_layers) for n in ("qkv_w", "o_w", "gate_up_w", "down_w")] + ["llama.lm_head"]
         return {"vit": vit, "proj": proj, "llama": llama}
@@ -244,10 +246,29 @@ class TeoWeights:
         self.gate_up_interleaved = True
         return self
 
+    def fold_vit_layernorm(self) -> "TeoWeights":
+        """LayerNorm folded into the linear that consumes it (include/teochat_b200.h: teo_gemm_bf16_ex): per ViT layer
+        qkv_wf = bf16(ln1_w ⊙ qkv_w), qkv_c = rowsum(qkv_wf) (f32), qkv_bf = qkv_w·ln1_b + qkv_b (f32), and fc1_* with ln2.
+        Runs once, before the blocked re-layout; the plain weights stay (exact mode, small batches)."""
+        if self.ln_folded or self.blocked.get("vit"):
+            return self
+        for i in range(self.cfg.vision.num_hidden_layers):
+            p = f"vit.{i}."
+            for lin, ln in (("qkv", "ln1"), ("fc1", "ln2")):
+                w, b = self.t[p + lin + "_w"].float(), self.t[p + lin + "_b"].float()
+                g, beta = self.t[p + ln + "_w"].float(), self.t[p + ln + "_b"].float()
+                wf = (w * g[None, :]).to(torch.bfloat16)
+                self.t[p + lin + "_wf"] = wf.contiguous()
+                self.t[p + lin + "_c"] = wf.float().sum(dim=1).contiguous()
+                self.t[p + lin + "_bf"] = (w @ beta + b).contiguous()
+        self.ln_folded = True
+        return self
+
     def to_blocked(self) -> "TeoWeights":
         """Re-lay every GEMM weight [N,K] as [N/128][K/64][128][64] (16 KiB contiguous operand tiles) when all
         matrices of a model part allow it; sets ``self.blocked[part]``.  Idempotent."""
         self.interleave_gate_up()
+        self.fold_vit_layernorm()
         for part, keys in self._gemm_weight_groups().items():
             if self.blocked.get(part):
                 continue

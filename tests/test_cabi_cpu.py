@@ -32,12 +32,12 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/teochat_b200.h but not exported"
     assert set(syms) == set(L.EXPORTS), "ctypes signature table and header disagree"
-    assert lib.teo_abi_version() == 3
+    assert lib.teo_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
     # pointer-sized fields, int fields in header order (catches drift between lib.py and the header)
-    assert C.sizeof(L.VitLayer) == 12 * C.sizeof(C.c_void_p)
+    assert C.sizeof(L.VitLayer) == 18 * C.sizeof(C.c_void_p)          # 12 parameters + the 6 folded-LayerNorm tensors
     assert C.sizeof(L.LlamaLayer) == 7 * C.sizeof(C.c_void_p)
     assert [f for f, _ in L.VitModel._fields_][:11] == ["hidden", "inter", "heads", "image", "patch", "kpad", "act", "layers_run", "eps",
                                                         "w_blocked", "exact"]

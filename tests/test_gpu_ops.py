@@ -502,3 +502,69 @@ def test_resize_feeds_the_tower_and_bad_args(teo):
     no_ws = ok[:11] + (None, 0, stream())
     assert lib.teo_resize_crop_normalize_u8(*no_ws) < 0 and b"workspace" in lib.teo_last_error()
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K,act,blocked", [(514, 3072, 1024, 0, True), (300, 4096, 1024, 1, True), (257 * 3, 384, 128, 0, False),
+                                               (1000, 128, 256, 2, False), (200, 64, 128, 0, False)])
+def test_gemm_folded_layernorm_and_row_stats(teo, M, N, K, act, blocked):
+    """teo_gemm_bf16_ex: LayerNorm folded into the consuming linear (HF CLIPEncoderLayer layer_norm1 → q/k/v, layer_norm2 → fc1,
+    modeling_image.py:136-151) against act(LayerNorm(x)·Wᵀ + b) in fp32, with the row statistics coming (a) from teo_row_stats
+    and (b) from the stats_out of a GEMM that produced x (residual epilogue) — the way teo_vit_encode chains them."""
+    lib, h = teo
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) * 1.5 + 0.7).to(torch.bfloat16)            # non-zero mean: the folded form subtracts mean·Σw
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    b = (torch.randn(N, generator=g) * 0.1).to(torch.bfloat16)
+    gamma = (1.0 + 0.1 * torch.randn(K, generator=g)).to(torch.bfloat16)
+    beta = (0.1 * torch.randn(K, generator=g)).to(torch.bfloat16)
+    eps = 1e-5
+    y = torch.nn.functional.layer_norm(x.float(), (K,), gamma.float(), beta.float(), eps)
+    want = y @ w.float().T + b.float()
+    want = want * torch.sigmoid(1.702 * want) if act == 1 else (torch.nn.functional.gelu(want) if act == 2 else want)
+    # folded tensors exactly as TeoWeights.fold_vit_layernorm builds them
+    wf = (w.float() * gamma.float()[None, :]).to(torch.bfloat16)
+    c = wf.float().sum(1).contiguous().to(DEV)
+    bf_ = (w.float() @ beta.float() + b.float()).contiguous().to(DEV)
+    xd, wfd = x.to(DEV), wf.to(DEV)
+    if blocked:
+        wb = torch.empty_like(wfd)
+        L.check(lib.teo_weight_to_blocked(wfd.data_ptr(), wb.data_ptr(), N, K, stream()))
+        wfd = wb
+    slots_in = 3
+    stats = torch.full((M, slots_in, 2), float("nan"), device=DEV)
+    L.check(lib.teo_row_stats(xd.data_ptr(), stats.data_ptr(), M, K, slots_in, stream()), "teo_row_stats")
+    st = stats.cpu()
+    assert torch.allclose(st[:, 0, 0], x.float().sum(1), rtol=1e-5, atol=1e-3) and torch.allclose(st[:, 0, 1], (x.float() ** 2).sum(1), rtol=1e-5)
+    assert (st[:, 1:] == 0).all()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    o = L.GemmOpts(act=act, w_blocked=int(blocked), ln_stats=stats.data_ptr(), ln_c=c.data_ptr(), ln_bias=bf_.data_ptr(), ln_slots=slots_in, ln_eps=eps)
+    L.check(lib.teo_gemm_bf16_ex(h, xd.data_ptr(), K, wfd.data_ptr(), K, out.data_ptr(), N, M, N, K, C.byref(o), None, 0, stream()), "teo_gemm_bf16_ex")
+    err = rel_err(out.cpu(), want)
+    print(f"folded LayerNorm GEMM {M}x{N}x{K} act {act}: rel err vs fp32 LayerNorm+Linear {err:.2e}")
+    assert err <= 2 ** -7
+    # (b) statistics emitted by a producing GEMM: x2 = a·w2ᵀ + residual, then the folded GEMM on x2
+    K2 = 192
+    a = (torch.randn(M, K2, generator=g)).to(torch.bfloat16).to(DEV)
+    w2 = (torch.randn(K, K2, generator=g) * K2 ** -0.5).to(torch.bfloat16).to(DEV)
+    res = xd.clone()
+    n_slots = lib.teo_gemm_stats_slots(M, K, K2)
+    assert n_slots >= 2
+    stats2 = torch.full((M, n_slots, 2), float("nan"), device=DEV)
+    o2 = L.GemmOpts(residual=res.data_ptr(), ldr=K, stats_out=stats2.data_ptr())
+    L.check(lib.teo_gemm_bf16_ex(h, a.data_ptr(), K2, w2.data_ptr(), K2, res.data_ptr(), K, M, K, K2, C.byref(o2), None, 0, stream()), "producer GEMM")
+    x2 = res.float().cpu()                                              # the bf16 rows as stored
+    s2 = stats2.cpu()
+    assert torch.isfinite(s2).all()
+    assert torch.allclose(s2[..., 0].sum(1), x2.sum(1), rtol=1e-5, atol=1e-2) and torch.allclose(s2[..., 1].sum(1), (x2 ** 2).sum(1), rtol=1e-4)
+    o3 = L.GemmOpts(act=act, w_blocked=int(blocked), ln_stats=stats2.data_ptr(), ln_c=c.data_ptr(), ln_bias=bf_.data_ptr(), ln_slots=n_slots, ln_eps=eps)
+    L.check(lib.teo_gemm_bf16_ex(h, res.data_ptr(), K, wfd.data_ptr(), K, out.data_ptr(), N, M, N, K, C.byref(o3), None, 0, stream()), "consumer GEMM")
+    want2 = torch.nn.functional.layer_norm(x2, (K,), gamma.float(), beta.float(), eps) @ w.float().T + b.float()
+    want2 = want2 * torch.sigmoid(1.702 * want2) if act == 1 else (torch.nn.functional.gelu(want2) if act == 2 else want2)
+    err2 = rel_err(out.cpu(), want2)
+    print(f"   … with statistics from the producing GEMM's epilogue ({n_slots} slots): rel err {err2:.2e}")
+    assert err2 <= 2 ** -7
+    # the folded path needs the tiled schedule: a small-M call is refused, not silently mis-served
+    small = L.GemmOpts(ln_stats=stats.data_ptr(), ln_c=c.data_ptr(), ln_bias=bf_.data_ptr(), ln_slots=slots_in, ln_eps=eps)
+    if N >= 256:
+        ws = torch.empty(lib.teo_gemm_workspace_bytes(8, N, K) + 16, dtype=torch.uint8, device=DEV)
+        assert lib.teo_gemm_bf16_ex(h, xd.data_ptr(), K, wfd.data_ptr(), K, out.data_ptr(), N, 8, N, K, C.byref(small), ws.data_ptr(), ws.numel(), stream()) != 0
