@@ -175,6 +175,16 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
                 }
             }
             __syncwarp();
+            // The chunk's 64 bias values first (8 × 16 bytes, the same addresses in every lane): issued together, their L1 / L2
+            // latency overlaps the TMEM read and the residual tile's arrival.  Loaded one group at a time inside the loop below they
+            // were eight dependent round trips per chunk — on the K = 1024 GEMMs of the ViT (short main loop, every linear has a
+            // bias) that made the epilogue, not the tensor pipe, the critical path.
+            uint4 bvec[8];
+            if (g.bias != nullptr && g.ln_stats == nullptr) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    bvec[c] = (n0 + c * 8 < g.N) ? *reinterpret_cast<const uint4*>(g.bias + n0 + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+            }
             uint32_t v0[32], v1[32];
             tmem_ld_32x32(t_acc + cj * 64, v0);
             tmem_ld_32x32(t_acc + cj * 64 + 32, v1);
@@ -200,7 +210,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] = fmaf(ln_rstd, x[j] - ln_mu * cc[j], bb[j]);
                 } else if (g.bias && n < g.N) {
-                    const uint4 bv = *reinterpret_cast<const uint4*>(g.bias + n);
+                    const uint4 bv = bvec[c];
                     const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }

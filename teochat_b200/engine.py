@@ -131,7 +131,9 @@ class TeoModel:
         p = lambda k: t[k].data_ptr()
         n_run = cfg.vit_layers_run
         self._vit_layers = (L.VitLayer * max(n_run, 1))()
-        fold = (not self.exact) and getattr(self.w, "ln_folded", False) and os.environ.get("TEO_VIT_LN_FOLD", "1") != "0"
+        # folded LayerNorm (teo_gemm_bf16_ex) is built and tested but OFF by default: measured 46.4 vs 43.7 ms per 256 frames — the
+        # K = 1024 GEMMs are epilogue-bound, and the folded epilogues cost more than the 46 LayerNorm passes they replace
+        fold = (not self.exact) and getattr(self.w, "ln_folded", False) and os.environ.get("TEO_VIT_LN_FOLD", "0") == "1"
         for i in range(n_run):
             for f, _ in L.VitLayer._fields_:
                 folded_field = f.endswith(("_wf", "_c", "_bf"))

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Iterator, Optional, Tuple
 
 import torch
@@ -268,7 +269,8 @@ class TeoWeights:
         """Re-lay every GEMM weight [N,K] as [N/128][K/64][128][64] (16 KiB contiguous operand tiles) when all
         matrices of a model part allow it; sets ``self.blocked[part]``.  Idempotent."""
         self.interleave_gate_up()
-        self.fold_vit_layernorm()
+        if os.environ.get("TEO_VIT_LN_FOLD", "0") == "1":       # optional path, off by default (engine._build_structs)
+            self.fold_vit_layernorm()
         for part, keys in self._gemm_weight_groups().items():
             if self.blocked.get(part):
                 continue

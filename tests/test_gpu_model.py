@@ -491,3 +491,30 @@ def test_decode_chain_bit_identical_to_kernel_per_gemm(case):
     assert launches_c < launches_k
     del model
     torch.cuda.empty_cache()
+
+
+def test_vit_folded_layernorm_path_matches_default(monkeypatch):
+    """The optional folded-LayerNorm ViT (TEO_VIT_LN_FOLD=1: teo_gemm_bf16_ex with gain-scaled weights, row statistics from the
+    out-proj / fc2 epilogues, no LayerNorm kernels) against the default path and the fp32 oracle at full CLIP-L width."""
+    from oracle import model as OM
+    from oracle import weights as OW
+    cfg = _full_width(1, 2)
+    frames = OW.synthetic_frames_u8(3, cfg.vision.image_size, 55)
+    base = _model(cfg, 77)
+    l0 = base.launch_count()
+    ref = base.encode_images(frames_u8=frames.to(DEV)).float().cpu()
+    n_default = base.launch_count() - l0
+    monkeypatch.setenv("TEO_VIT_LN_FOLD", "1")
+    folded = _model(cfg, 77)
+    assert folded.w.ln_folded and "vit.0.qkv_wf" in folded.w.t
+    l0 = folded.launch_count()
+    got = folded.encode_images(frames_u8=frames.to(DEV)).float().cpu()
+    n_folded = folded.launch_count() - l0
+    sd = OW.make_state_dict(cfg, 77, prefixes=[OM.VIT, "model.mm_projector"])
+    want = OM.encode_images(sd, cfg, OM.normalize_u8_nhwc(frames), "fp32")
+    e_def, e_fold, e_pair = _rel(ref, want), _rel(got, want), _rel(got, ref)
+    print(f"ViT+projector vs fp32 oracle: default {e_def:.2e}, folded LayerNorm {e_fold:.2e}; folded vs default {e_pair:.2e}; "
+          f"launches {n_default} -> {n_folded}")
+    assert e_fold <= 1e-2 and e_pair <= 1e-2 and n_folded < n_default
+    del base, folded
+    torch.cuda.empty_cache()
