@@ -255,7 +255,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            if (!SK && g.tma_epi) {             // (the stream-K instantiation has no staging buffer)
+            if (!SK && g.tma_epi) {             // (the stream-K instantiation has no staging buffer and never runs this epilogue)
                 staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, m_blk, n_blk, stg, rbar, rph, lane, q, hsel, [&] {
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[as]);

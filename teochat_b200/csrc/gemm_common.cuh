@@ -60,9 +60,15 @@ template <int BN, bool SK = false>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+#ifdef TEO_SK_RING8            // A/B build (build.build_variant("sk8", ["TEO_SK_RING8"])): the round-1 ring depth for the stream-K schedule
+    static constexpr int STAGING = STAGING_BYTES;
+    static constexpr int BUDGET = 196608;
+    static constexpr int MAX_STAGES = 8;
+#else
     static constexpr int STAGING = SK ? 0 : STAGING_BYTES;
     static constexpr int BUDGET = SK ? 229376 : 196608;
     static constexpr int MAX_STAGES = SK ? 11 : 8;
+#endif
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
