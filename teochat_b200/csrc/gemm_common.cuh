@@ -53,21 +53,23 @@ struct GemmArgs {
     unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 
-// SK = the small-M stream-K schedule (decode): partial outputs go straight from registers to global memory, so the epilogue
-// staging buffer is dropped and its 32 KiB go to the ring — the weight stream is latency-bound (bytes in flight per SM × 148 /
-// HBM latency), measured 5.1 TB/s with 8 stages of 16 KiB weights per SM (profiles/r02_dec_gemm_skew.txt).
+// SK = the small-M stream-K schedule (decode).  Its partial outputs go straight from registers to global memory, so the epilogue
+// staging buffer could go to the ring instead (TEO_SK_DEEP: 11 / 9 / 7 stages for BN = 32 / 64 / 128 instead of 8 / 8 / 6).  Built and
+// A/B-measured on one box, alternating runs (build.build_variant("skdeep", ["TEO_SK_DEEP"]), scripts/gpu_r02_ring.sh): the deeper
+// ring is 1.0 % SLOWER on the decode step at bs=32 (2401 vs 2378 ms per 255 steps, 3 runs each), 2.3 % at bs=2 — more weight
+// requests in flight per SM do not raise the 5.1 TB/s the stream reaches (profiles/r02_dec_gemm_skew.txt).  Default: round-1 depth.
 template <int BN, bool SK = false>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-#ifdef TEO_SK_RING8            // A/B build (build.build_variant("sk8", ["TEO_SK_RING8"])): the round-1 ring depth for the stream-K schedule
-    static constexpr int STAGING = STAGING_BYTES;
-    static constexpr int BUDGET = 196608;
-    static constexpr int MAX_STAGES = 8;
-#else
+#ifdef TEO_SK_DEEP
     static constexpr int STAGING = SK ? 0 : STAGING_BYTES;
     static constexpr int BUDGET = SK ? 229376 : 196608;
     static constexpr int MAX_STAGES = SK ? 11 : 8;
+#else
+    static constexpr int STAGING = STAGING_BYTES;
+    static constexpr int BUDGET = 196608;
+    static constexpr int MAX_STAGES = 8;
 #endif
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
