@@ -145,8 +145,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         g.trace[blockIdx.x * 8 + 1] = smid;
     }
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == 0 || (warp == 3 && g.producers == 2)) {
+        // ------------------------------------------------------------------ TMA producer(s)
+        // g.producers == 2 (stream-K decode GEMMs, TEO_SK_PRODUCERS=2): warp 3, otherwise idle, is a second producer — the two take
+        // alternate k-blocks of the CTA's share (same schedule, same ring positions), doubling the rate at which one SM can issue
+        // TMA requests; each full barrier is still armed and fed by exactly one of them.
+        const int pid = warp == 3 ? 1 : 0, np = g.producers == 2 ? 2 : 1;
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
@@ -172,6 +176,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 int cnt = 0;
                 while (cnt < STAGES && sc.next(g, it)) {
                     for (int kb = it.kb0; kb < it.kb1 && cnt < STAGES; ++kb, ++cnt) {
+                        if (cnt % np != pid) continue;
                         mbar_arrive_expect_tx(&full_bar[cnt], Cfg::STAGE_BYTES);
                         if (g.w_is_a) load_a(cnt, kb, it.m_blk);
                         else load_b(cnt, kb, it.n_blk);
@@ -179,23 +184,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 pre = cnt;
             }
-            trace_stamp(g, 2);                   // ring filled with weight tiles
+            if (pid == 0) trace_stamp(g, 2);     // ring filled with weight tiles
             pdl_wait();
-            trace_stamp(g, 3);                   // predecessor grid complete
+            if (pid == 0) trace_stamp(g, 3);     // predecessor grid complete
             int done = 0;
             Scheduler sc;
             sc.init(g, num_m, num_n, total_kb);
             WorkItem it;
             while (sc.next(g, it)) {
                 for (int kb = it.kb0; kb < it.kb1; ++kb, ++done) {
-                    if (done < pre) {               // weights already in flight: add the other operand
-                        if (g.w_is_a) load_b(s, kb, it.n_blk);
-                        else load_a(s, kb, it.m_blk);
-                    } else {
-                        mbar_wait(&empty_bar[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                        load_a(s, kb, it.m_blk);
-                        load_b(s, kb, it.n_blk);
+                    if (done % np == pid) {
+                        if (done < pre) {               // weights already in flight: add the other operand
+                            if (g.w_is_a) load_b(s, kb, it.n_blk);
+                            else load_a(s, kb, it.m_blk);
+                        } else {
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                            load_a(s, kb, it.m_blk);
+                            load_b(s, kb, it.n_blk);
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -478,6 +485,15 @@ bool gemm_pair_enabled();
 int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
                      const GemmArgs& g, cudaStream_t stream);
 
+// TMA producer threads per CTA in the stream-K (decode) schedule: TEO_SK_PRODUCERS=1|2
+static int sk_producers() {
+    static const int n = [] {
+        const char* e = getenv("TEO_SK_PRODUCERS");
+        return (e && e[0] == '2') ? 2 : 1;
+    }();
+    return n;
+}
+
 struct GemmPlan {
     bool swap;
     int bn;
@@ -550,6 +566,7 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     g.transposed = 1;
     g.streamk = 1;
     g.sk_q = p.sk_q;
+    g.producers = sk_producers();
     g.w_is_a = 1;
     g.C = workspace;
     g.ldc = N;
@@ -649,6 +666,7 @@ int teo::launch_gemm(teo_handle* h, const bf16* A, int lda, const bf16* W, int l
             }
             g.streamk = 1;
             g.sk_q = p.sk_q;
+            g.producers = sk_producers();
             g.C = workspace;
             g.ldc = N;                       // partial layout [slot][M_act][N_out]
             g.split_stride = static_cast<long long>(M) * N;

@@ -35,6 +35,7 @@ struct GemmArgs {
     int tma_epi;                // bf16 row-major output through the staged TMA-store epilogue
     int w_is_a;                 // operand A holds the (constant) weights: may be fetched before griddepcontrol.wait
     int w_blocked;              // weights stored tile-blocked [N/128][K/64][128][64] (4-D tensor map)
+    int producers;              // stream-K schedule: 2 = a second TMA producer warp shares the k-blocks (gemm.cu)
     int k_wrap;                 // > 0: the WEIGHT operand has only k_wrap k-blocks and k-block kb reads kb % k_wrap — the
                                 // activation operand then holds K/k_wrap/64 bf16 planes side by side (exact mode: an fp32
                                 // activation split into hi | mid | lo bf16 terms, all multiplied by the same weights)
