@@ -89,11 +89,18 @@ class TeoModel:
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
         try:
+            self._release_kv_allocator()
             if getattr(self, "_h", None):
                 self.lib.teo_destroy(self._h)
                 self._h = None
         except Exception:
             pass
+
+    def _release_kv_allocator(self):
+        a = getattr(self, "_kv_alloc", None)
+        if a:
+            self.lib.teo_kv_destroy(a)
+        self._kv_alloc = None
 
     def set_pdl(self, enabled: bool):
         """Programmatic dependent launch inside the decode step (default on; results are identical)."""
@@ -355,16 +362,14 @@ class TeoModel:
         v_last[:] = cu[1:] - 1
         v_len[:] = lens
         v_bt[:] = 0
+        self._release_kv_allocator()                      # (left behind only if a previous call raised half-way)
         alloc = C.c_void_p()
         L.check(self.lib.teo_kv_create(n_pages, C.byref(alloc)), "teo_kv_create")
-        try:
-            for b in range(B):
-                got = self.lib.teo_kv_alloc(alloc, lens[b] + max_new_tokens, ps, v_bt[b].ctypes.data_as(C.POINTER(C.c_int)), max_pages)
-                if got != pages_per[b]:
-                    L.check(got if got < 0 else -1, "teo_kv_alloc")
-        except Exception:
-            self.lib.teo_kv_destroy(alloc)
-            raise
+        self._kv_alloc = alloc
+        for b in range(B):
+            got = self.lib.teo_kv_alloc(alloc, lens[b] + max_new_tokens, ps, v_bt[b].ctypes.data_as(C.POINTER(C.c_int)), max_pages)
+            if got != pages_per[b]:
+                L.check(got if got < 0 else -1, "teo_kv_alloc")
         self._ensure_kv(n_pages)
         meta_h = torch.from_numpy(meta).pin_memory()
         meta_d = meta_h.to(dev, non_blocking=True)
@@ -475,7 +480,7 @@ class TeoModel:
         toks = st.tokens.cpu().numpy()
         for r, orig in enumerate(rows):
             result[orig] = toks[r]
-        self.lib.teo_kv_destroy(alloc)
+        self._release_kv_allocator()
         _nvtx(None)
         if ev:
             torch.cuda.synchronize(dev)
