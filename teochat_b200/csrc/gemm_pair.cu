@@ -30,11 +30,19 @@ namespace teo {
 
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_HALF_B_BYTES = (PAIR_BN / 2) * BK * 2;              // 16 KiB: this CTA's half of the W tile
-constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 KiB
-constexpr int PAIR_STAGES = 6;
-constexpr int PAIR_TMEM_COLS = 2 * PAIR_BN;                             // two accumulator stages
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+constexpr int PAIR_TMEM_COLS = 2 * PAIR_BN;                             // MT = 1: two accumulator stages; MT = 2: the two row sub-tiles
 constexpr int PAIR_GROUP_M = 16;                                        // 256-row tile rows per rasterisation group (4096 rows of A)
+// MT = row sub-tiles per pair tile.  MT = 1: 256 × 256 tiles, two TMEM accumulator stages (the epilogue of a tile overlaps the next
+// tile's MMAs).  MT = 2: 512 × 256 tiles — both accumulators belong to ONE tile, every W k-block is used by two MMAs, so the
+// operand bytes fetched per flop drop by a quarter (48 KiB per 2·128·256·64 MACs instead of 32 KiB per 128·256·64): the main loop
+// of the 256 × 256 tiling is bound by what the L2 slices can deliver, at the price of an epilogue that no longer
+// overlaps (long-K GEMMs only).
+template <int MT>
+struct PairCfg {
+    static constexpr int STAGE_BYTES = MT * A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 / 48 KiB
+    static constexpr int STAGES = MT == 1 ? 6 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
 
 struct PairTile {
     int m2, n_blk;
@@ -69,16 +77,19 @@ __device__ __forceinline__ PairTile pair_tile(int unit, int num_m2, int num_n, i
     return {first_m + in_sup % gm, first_n + in_sup / gm};
 }
 
+template <int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs g) {
     constexpr int BN = PAIR_BN;
-    constexpr int STAGES = PAIR_STAGES;
+    constexpr int STAGES = PairCfg<MT>::STAGES;
+    constexpr int A_BYTES = MT * A_STAGE_BYTES;              // this CTA's A rows of one k-block: MT sub-tiles of 128 rows
+    constexpr int ACC_STAGES = MT == 1 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* staging = smem + STAGES * PAIR_STAGE_BYTES;
+    uint8_t* smem_b = smem + STAGES * A_BYTES;
+    uint8_t* staging = smem + STAGES * PairCfg<MT>::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);     // used in the leader only
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -91,7 +102,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int lane = threadIdx.x & 31;
     const int rank = static_cast<int>(cluster_ctarank());
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int num_m2 = (g.M + 2 * BM - 1) / (2 * BM);
+    const int num_m2 = (g.M + MT * 2 * BM - 1) / (MT * 2 * BM);          // pair tiles along M (MT · 256 rows each)
     const int num_n = (g.N + BN - 1) / BN;
     const int total_kb = (g.K + BK - 1) / BK;
     const int units = num_m2 * num_n;
@@ -135,16 +146,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t hint_w = g.raster == 0 ? h_stream : h_stay;
             for (int unit = pair; unit < units; unit += n_pairs) {
                 const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
-                const int m_blk = t.m2 * 2 + rank;
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * PairCfg<MT>::STAGE_BYTES);
+#pragma unroll
+                    for (int sub = 0; sub < MT; ++sub) {             // this CTA's 128 rows of every 256-row sub-tile
+                        const int m_blk = (t.m2 * MT + sub) * 2 + rank;
+                        uint8_t* dst = smem_a + s * A_BYTES + sub * A_STAGE_BYTES;
+                        if (g.l2_hint) tma_load_2d_pair_hint(dst, &tma_a, &full_bar[s], kb * BK, m_blk * BM, hint_a);
+                        else tma_load_2d_pair(dst, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
+                    }
                     if (g.l2_hint) {
-                        tma_load_2d_pair_hint(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM, hint_a);
                         if (g.w_blocked) tma_load_4d_pair_hint(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank, hint_w);
                         else tma_load_2d_pair_hint(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2), hint_w);
                     } else {
-                        tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tma_a, &full_bar[s], kb * BK, m_blk * BM);
                         if (g.w_blocked) tma_load_4d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], 0, 0, kb, t.n_blk * 2 + rank);
                         else tma_load_2d_pair(smem_b + s * PAIR_HALF_B_BYTES, &tma_b, &full_bar[s], kb * BK, t.n_blk * BN + rank * (BN / 2));
                     }
@@ -162,19 +177,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int unit = pair; unit < units; unit += n_pairs) {
                 mbar_wait(&tempty_bar[as], aph ^ 1);             // both CTAs' epilogues have drained this accumulator stage
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + (MT == 1 ? as * BN : 0);
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);                 // both CTAs' halves of the stage have landed
                     tc_fence_after();
-                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
                     const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + s * PAIR_HALF_B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int sub = 0; sub < MT; ++sub) {         // MT = 2: the W k-block feeds both row sub-tiles (accumulators sub · 256)
+                        const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + s * A_BYTES + sub * A_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_pair(d_tmem + sub * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit_pair(&empty_bar[s], 3);          // frees the ring slot in both CTAs when the MMAs retire
                     if (kb == total_kb - 1) umma_commit_pair(&tfull_bar[as], 3);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                if (++as == 2) { as = 0; aph ^= 1; }
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
             }
         }
         __syncwarp();
@@ -193,12 +212,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, t.m2 * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
-                tc_fence_before();
-                mbar_arrive_leader(&tempty_bar[as]);
-            });
-            if (++as == 2) { as = 0; aph ^= 1; }
+            const uint32_t lanes = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+            if constexpr (MT == 1) {
+                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes + as * BN, t.m2 * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
+                    tc_fence_before();
+                    mbar_arrive_leader(&tempty_bar[as]);
+                });
+            } else {
+                // the two row sub-tiles one after the other; the accumulators are handed back after the LAST read of the second
+                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes, (t.m2 * MT) * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [] {});
+                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes + BN, (t.m2 * MT + 1) * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
+                    tc_fence_before();
+                    mbar_arrive_leader(&tempty_bar[as]);
+                });
+            }
+            if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -231,10 +259,17 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
                      const GemmArgs& g, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        TEO_CUDA(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+        TEO_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<1>::SMEM_BYTES));
+        TEO_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<2>::SMEM_BYTES));
         attr_set = true;
     }
-    const int units = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
+    // 512-row pair tiles for long contractions over many rows (LLaMA prefill, ViT fc2); TEO_PAIR_MT=1|2 forces one (A/B)
+    static const int env_mt = [] {
+        const char* e = getenv("TEO_PAIR_MT");
+        return e ? atoi(e) : 0;
+    }();
+    const int mt = env_mt == 1 || env_mt == 2 ? env_mt : ((g.K >= 2048 && g.M >= 8192) ? 2 : 1);
+    const int units = ((g.M + mt * 2 * BM - 1) / (mt * 2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
     const int pairs = std::max(1, std::min(units, h->num_sms / 2));
     // Rasterisation group: W is re-read from HBM once per group of tile rows, so bigger groups mean less DRAM traffic (and
     // power — the prefill GEMMs run power-capped) until the A panels of a group no longer stay in L2 beside the W stream.
@@ -257,11 +292,12 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
         return e ? atoi(e) : 0;
     }();
     GemmArgs ga = g;
-    ga.sk_q = g_pair_cfg[0] > 0 ? g_pair_cfg[0] : env_group_m;      // (stream-K field, unused by this kernel: carries the group size)
+    ga.sk_q = g_pair_cfg[0] > 0 ? g_pair_cfg[0] : std::max(1, env_group_m / mt);      // (stream-K field, unused by this kernel: carries the group size in pair tiles)
     ga.group_n = g_pair_cfg[1] > 0 ? g_pair_cfg[1] : env_group_n;
     ga.raster = g_pair_cfg[2] >= 0 ? g_pair_cfg[2] : env_raster;
     ga.l2_hint = g_pair_cfg[3] >= 0 ? g_pair_cfg[3] : env_hint;
-    TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, ta, tb, tc, tr, ga));
+    if (mt == 2) TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel<2>, dim3(2 * pairs), dim3(GEMM_THREADS), PairCfg<2>::SMEM_BYTES, stream, ta, tb, tc, tr, ga));
+    else TEO_CUDA(launch_kc(PDL_GEMM, gemm_pair_kernel<1>, dim3(2 * pairs), dim3(GEMM_THREADS), PairCfg<1>::SMEM_BYTES, stream, ta, tb, tc, tr, ga));
     TEO_LAUNCH_CHECK("gemm_pair_kernel");
     h->launches++;
     return TEO_OK;

@@ -41,6 +41,8 @@ GEMM_SHAPES = [
     (128, 256, 64), (256, 512, 128), (300, 1024, 1024), (257 * 3, 3072, 1024), (1000, 4096, 640),
     (200, 128, 256), (130, 64, 128), (513, 328, 200),
     (1, 4096, 4096), (5, 512, 256), (32, 12288, 4096), (32, 4096, 11008), (64, 1024, 512), (100, 32000, 512), (17, 256, 64),
+    # long K over many rows: the 512-row pair tiles (gemm_pair_kernel<2>), M not a multiple of 512 / 256 / 128
+    (8200, 768, 2048), (8977, 512, 4096),
 ]
 
 
@@ -106,6 +108,31 @@ def test_gemm_swiglu_pairs_epilogue(teo, M, I, K, blocked):
     rc = lib.teo_gemm_bf16(h, A.data_ptr(), K, W_int.data_ptr(), K, out.data_ptr(), I, 32, 2 * I, K, None, None, 0, L.ACT_SWIGLU_PAIRS, 0,
                            None, 0, stream())
     assert rc == -4 and b"tiled schedule" in lib.teo_last_error()
+
+
+def test_gemm_512_row_pair_tiles_with_epilogues(teo):
+    """gemm_pair_kernel<2> (M >= 8192, K >= 2048: two 256-row sub-tiles per pair tile, one shared W k-block) with the epilogues the
+    prefill uses on it: residual (o / down), SwiGLU pairs (gate/up), bias + activation."""
+    lib, h = teo
+    M, N, K = 8300, 1024, 2048
+    A, W = bf(rnd(M, K, seed=3)), bf(rnd(N, K, scale=K ** -0.5, seed=4))
+    bias, res = bf(rnd(N, scale=0.1, seed=5)), bf(rnd(M, N, seed=6))
+    ref = A.float() @ W.float().t()
+    assert rel_err(gemm(teo, A, W, bias=bias, residual=res), ref + bias.float() + res.float()) < 1e-2
+    x = ref + bias.float()
+    assert rel_err(gemm(teo, A, W, bias=bias, act=1), x * torch.sigmoid(1.702 * x)) < 1e-2
+    inplace = res.clone()                                       # residual aliasing the output, as the o / down projections run
+    gemm(teo, A, W, residual=inplace, C_out=inplace)
+    assert rel_err(inplace, ref + res.float()) < 1e-2
+    # SwiGLU pairs: rows interleaved in blocks of 32 (gate 32 | up 32)
+    I = N // 2
+    g_, u_ = W[:I].float(), W[I:].float()
+    Wi = torch.stack([W[:I].view(I // 32, 32, K), W[I:].view(I // 32, 32, K)], dim=1).reshape(N, K).contiguous()
+    gg, uu = bf(A.float() @ g_.t()).float(), bf(A.float() @ u_.t()).float()
+    want = torch.nn.functional.silu(gg) * uu
+    out = torch.empty(M, I, dtype=torch.bfloat16, device=A.device)
+    L.check(lib.teo_gemm_bf16(h, A.data_ptr(), K, Wi.data_ptr(), K, out.data_ptr(), I, M, N, K, None, None, 0, 3, 0, None, 0, stream()), "swiglu pairs")
+    assert rel_err(out, want) < 2e-2
 
 
 def test_gemm_strided_operands(teo):
