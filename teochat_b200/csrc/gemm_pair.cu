@@ -263,12 +263,15 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
         TEO_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<2>::SMEM_BYTES));
         attr_set = true;
     }
-    // 512-row pair tiles for long contractions over many rows (LLaMA prefill, ViT fc2); TEO_PAIR_MT=1|2 forces one (A/B)
+    // 512-row pair tiles for long contractions over many rows; TEO_PAIR_MT=1|2 forces one, a value >= 1024 sets the K threshold (A/B)
     static const int env_mt = [] {
         const char* e = getenv("TEO_PAIR_MT");
         return e ? atoi(e) : 0;
     }();
-    const int mt = env_mt == 1 || env_mt == 2 ? env_mt : ((g.K >= 2048 && g.M >= 8192) ? 2 : 1);
+    // Rule: MT = 2 only where the un-overlapped epilogue of two sub-tiles (≈ 12 k cycles) is small against the main loop — the down
+    // projection (K = 11008: −7 % stand-alone); at K = 4096 the gate/up (SwiGLU) and o (residual) GEMMs lose what the operand
+    // traffic gains (same-box A/B, scripts/gpu_r02_mt.sh: prefill 816.8 → 807.9 ms with MT = 2 on every K ≥ 2048 GEMM).
+    const int mt = env_mt == 1 || env_mt == 2 ? env_mt : ((g.K >= (env_mt >= 1024 ? env_mt : 8192) && g.M >= 8192) ? 2 : 1);
     const int units = ((g.M + mt * 2 * BM - 1) / (mt * 2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
     const int pairs = std::max(1, std::min(units, h->num_sms / 2));
     // Rasterisation group: W is re-read from HBM once per group of tile rows, so bigger groups mean less DRAM traffic (and
