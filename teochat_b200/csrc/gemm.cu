@@ -249,7 +249,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int ew = warp - 4;                 // 0..7
         const int q = ew & 3;                    // TMEM lane quadrant this warp may access (= warp % 4)
         const int hsel = ew >> 2;                // which column chunks of the tile this warp owns
-        uint8_t* stg = staging + ew * 4096;
+        uint8_t* stg = staging + ew * 4096 * EPI_BUFS;
         uint64_t* rbar = &res_bar[ew];
         uint32_t rph = 0;
         int as = 0;

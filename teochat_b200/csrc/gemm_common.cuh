@@ -15,7 +15,14 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int GEMM_THREADS = 384;     // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
-constexpr int STAGING_BYTES = EPI_WARPS * 4096;   // per warp: 32 rows × 64 bf16 (128 B, swizzled)
+// Epilogue staging: per warp EPI_BUFS buffers of 32 rows × 64 bf16 (128 B rows, swizzled).  With two, a chunk is converted and staged
+// while the previous chunk's TMA store is still reading its buffer (cp.async.bulk.wait_group.read 1 instead of 0): the epilogue of a tile
+// no longer pays one store-drain latency per chunk — what made the un-overlapped epilogue of the 512-row pair tiles expensive.
+#ifndef TEO_EPI_BUFS
+#define TEO_EPI_BUFS 2
+#endif
+constexpr int EPI_BUFS = TEO_EPI_BUFS;
+constexpr int STAGING_BYTES = EPI_WARPS * 4096 * EPI_BUFS;
 constexpr int GROUP_M = 16;     // rasterisation group (tiles along M sharing W tiles in L2)
 
 struct GemmArgs {
@@ -68,8 +75,8 @@ struct GemmCfg {
     static constexpr int BUDGET = SK ? 229376 : 196608;
     static constexpr int MAX_STAGES = SK ? 11 : 8;
 #else
-    static constexpr int STAGING = STAGING_BYTES;
-    static constexpr int BUDGET = 196608;
+    static constexpr int STAGING = SK ? 0 : STAGING_BYTES;                 // (the stream-K epilogue stores straight from registers)
+    static constexpr int BUDGET = SK ? 196608 : 229376 - STAGING_BYTES;    // ring: 8 / 8 / 6 stages (SK), 8 / 6 / 5 / 3 (tiled, BN 32 … 256)
     static constexpr int MAX_STAGES = 8;
 #endif
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
@@ -104,8 +111,14 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // (gemm_pair.cu), whose CTAs each own 128 rows of a 256-row tile.
 template <int BN, typename Release>
 __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CUtensorMap* tma_c, const CUtensorMap* tma_r, uint32_t t_acc,
-                                                     int m_blk, int n_blk, uint8_t* stg, uint64_t* rbar, uint32_t& rph, int lane, int q,
+                                                     int m_blk, int n_blk, uint8_t* stg_base, uint64_t* rbar, uint32_t& rph, int lane, int q,
                                                      int hsel, Release release) {
+    // rph carries two counters: bit 0 = phase of the residual barrier, bits 1.. = chunks staged so far (selects the staging buffer)
+    auto next_buf = [&]() -> uint8_t* {
+        uint8_t* b = stg_base + ((rph >> 1) % EPI_BUFS) * 4096;
+        rph += 2;
+        return b;
+    };
     if (g.act == TEO_ACT_SWIGLU_PAIRS) {
         // ---- SwiGLU fused into the gate/up projection: the weight rows come interleaved in blocks of 32
         // (…| gate 32 | up 32 |…), so accumulator columns [c, c+32) and [c+32, c+64) are the gate and the up
@@ -117,7 +130,8 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
         for (int oc = hsel; oc < BN / 128; oc += 2) {
             const int n_out0 = n_blk * (BN / 2) + oc * 64;
             if (2 * n_out0 >= g.N) break;              // warp-uniform
-            if (lane == 0) tma_store_wait_read<0>();   // previous store has drained the staging buffer
+            uint8_t* stg = next_buf();
+            if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this staging buffer has drained it
             __syncwarp();
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
@@ -176,8 +190,9 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
         for (int cj = hsel; cj < BN / 64; cj += 2) {
             const int n0 = n_blk * BN + cj * 64;
             if (n0 >= g.N) break;                      // warp-uniform
+            uint8_t* stg = next_buf();
             if (lane == 0) {
-                tma_store_wait_read<0>();              // previous store has drained the staging buffer
+                tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this staging buffer has drained it
                 if (has_res) {
                     mbar_arrive_expect_tx(rbar, 4096);
                     tma_load_2d(stg, tma_r, rbar, n0, row0);
@@ -202,7 +217,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
                 release();
             }
             if (has_res) {
-                mbar_wait(rbar, rph);
+                mbar_wait(rbar, rph & 1);
                 rph ^= 1;
             }
 #pragma unroll

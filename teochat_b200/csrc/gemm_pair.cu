@@ -40,7 +40,7 @@ constexpr int PAIR_GROUP_M = 16;                                        // 256-r
 template <int MT>
 struct PairCfg {
     static constexpr int STAGE_BYTES = MT * A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 / 48 KiB
-    static constexpr int STAGES = MT == 1 ? 6 : 4;
+    static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;          // 6 / 4 with one staging buffer per warp, 5 / 3 with two
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
@@ -203,7 +203,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int ew = warp - 4;
         const int q = ew & 3;
         const int hsel = ew >> 2;
-        uint8_t* stg = staging + ew * 4096;
+        uint8_t* stg = staging + ew * 4096 * EPI_BUFS;
         uint64_t* rbar = &res_bar[ew];
         uint32_t rph = 0;
         int as = 0;
