@@ -201,39 +201,70 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The WHOLE warp walks the schedule in convergent control flow and only the tcgen05 instructions are issued by one elected
+        // lane.  Every value the descriptors are built from is made provably warp-uniform (item fields are broadcast from lane 0),
+        // so the compiler keeps descriptors and loop state in uniform registers.  Issued from inside `if (lane == 0)` each of the
+        // 16 MMAs of a (tile, key block) cost a ≈ 16-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY loop, and the single issuing
+        // thread — not the tensor pipe, not the softmax — bounded the kernel: with the softmax removed it ran at 842 TFLOP/s
+        // (`profiles/r02_flash_issue.txt`).
+        {
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN_MAJOR;
+            const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
             uint32_t kv_cnt = 0, q_cnt = 0, n_t[2] = {0, 0};
             for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-                const FaItem it = fa_decode<CAUSAL, BN>(g, idx);
+                FaItem it = fa_decode<CAUSAL, BN>(g, idx);
+                it.valid = __shfl_sync(0xffffffffu, static_cast<int>(it.valid), 0) != 0;
                 if (!it.valid) continue;
+                it.seqlen = __shfl_sync(0xffffffffu, it.seqlen, 0);
+                it.n_tiles = __shfl_sync(0xffffffffu, it.n_tiles, 0);
+                it.nb[0] = __shfl_sync(0xffffffffu, it.nb[0], 0);
+                it.nb[1] = __shfl_sync(0xffffffffu, it.nb[1], 0);
+                it.nb_max = max(it.nb[0], it.nb[1]);
                 const int qs = q_cnt % Q_SETS;
-                const uint8_t* sQi = sQ + qs * Cfg::Q_SET;
+                const uint32_t sQi = sQ_u + qs * Cfg::Q_SET;
                 auto issue_s = [&](int t, int stage, int cols) {           // S_t = Q_t · K(stage)ᵀ   [128 × cols]
                     const uint32_t idesc = umma_idesc_bf16(128, cols);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) {
-                        const uint64_t a = umma_desc_k_sw128(smem_u32(sQi + (t * HALVES + ks / 4) * FA_TILE_BYTES)) + 2 * (ks & 3);
-                        const uint64_t b = umma_desc_k_sw128(smem_u32(sK + stage * KV_TILE + (ks / 4) * HALF_BYTES)) + 2 * (ks & 3);
-                        umma_bf16(tmem_base + TM_S + BN * t, a, b, idesc, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < HD / 16; ++ks) {
+                            const uint64_t a = umma_desc_k_sw128(sQi + (t * HALVES + ks / 4) * FA_TILE_BYTES) + 2 * (ks & 3);
+                            const uint64_t b = umma_desc_k_sw128(sK_u + stage * KV_TILE + (ks / 4) * HALF_BYTES) + 2 * (ks & 3);
+                            umma_bf16(tmem_base + TM_S + BN * t, a, b, idesc, ks > 0 ? 1u : 0u);
+                        }
                     }
+                    __syncwarp();
                 };
                 auto issue_pv = [&](int t, int stage, int cols, bool first) {   // O_t (+)= P_t · V(stage)   [128 × HD]
-                    const uint32_t vbase = smem_u32(sV + stage * KV_TILE);
-                    for (int ks = 0; ks < cols / 16; ++ks) {
-                        const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, HALF_BYTES, 1024);
-                        umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + BN * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                    const uint32_t vbase = sV_u + stage * KV_TILE;
+                    if (elect_one()) {
+                        if (cols == BN) {
+#pragma unroll
+                            for (int ks = 0; ks < BN / 16; ++ks) {
+                                const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, HALF_BYTES, 1024);
+                                umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + BN * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < cols / 16; ++ks) {
+                                const uint64_t b = umma_desc_mn_sw128(vbase + ks * 2048, HALF_BYTES, 1024);
+                                umma_bf16_ts(tmem_base + TM_O + HD * t, tmem_base + TM_S + BN * t + 8 * ks, b, idesc_pv, (first && ks == 0) ? 0u : 1u);
+                            }
+                        }
                     }
+                    __syncwarp();
+                };
+                auto commit = [&](uint64_t* bar) {
+                    if (elect_one()) umma_commit(bar);
+                    __syncwarp();
                 };
                 mbar_wait(&q_full[qs], (q_cnt / Q_SETS) & 1);
                 mbar_wait(&k_full[kv_cnt % STAGES], (kv_cnt / STAGES) & 1);
                 tc_fence_after();
                 for (int t = 0; t < it.n_tiles; ++t) {
                     issue_s(t, kv_cnt % STAGES, fa_block_cols<BN>(it.seqlen, 0));
-                    umma_commit(&s_full[t]);
+                    commit(&s_full[t]);
                 }
-                umma_commit(&k_empty[kv_cnt % STAGES]);
-                if (it.nb_max == 1) umma_commit(&q_empty[qs]);
+                commit(&k_empty[kv_cnt % STAGES]);
+                if (it.nb_max == 1) commit(&q_empty[qs]);
                 for (int j = 0; j < it.nb_max; ++j) {
                     const uint32_t cv = kv_cnt + j, ck = cv + 1;
                     const int sv = cv % STAGES, sk = ck % STAGES;
@@ -249,17 +280,17 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                         }
                         tc_fence_after();
                         issue_pv(t, sv, cols, j == 0);
-                        if (j == it.nb[t] - 1) umma_commit(&o_full[t]);
+                        if (j == it.nb[t] - 1) commit(&o_full[t]);
                         if (j + 1 < it.nb[t]) {
                             mbar_wait(&k_full[sk], (ck / STAGES) & 1);
                             tc_fence_after();
                             issue_s(t, sk, fa_block_cols<BN>(it.seqlen, j + 1));
-                            umma_commit(&s_full[t]);
+                            commit(&s_full[t]);
                         }
                     }
-                    umma_commit(&v_empty[sv]);
-                    if (j + 1 < it.nb_max) umma_commit(&k_empty[sk]);
-                    if (j + 2 == it.nb_max) umma_commit(&q_empty[qs]);     // the item's last Q·Kᵀ has been issued
+                    commit(&v_empty[sv]);
+                    if (j + 1 < it.nb_max) commit(&k_empty[sk]);
+                    if (j + 2 == it.nb_max) commit(&q_empty[qs]);     // the item's last Q·Kᵀ has been issued
                 }
                 kv_cnt += it.nb_max;
                 ++q_cnt;
@@ -407,6 +438,17 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                 const bool need_mask = (kv0 + cols > seqlen) || (CAUSAL && kv0 + cols - 1 > it.m0 + 128 * t);
                 mbar_wait(&s_full[t], n_blk & 1);
                 tc_fence_after();
+                // The element-wise mask must stay a (warp-uniform) BRANCH: only the one or two blocks per query tile on the diagonal or
+                // at the sequence end need it.  Written as plain conditional assignments the compiler if-converted the compares and
+                // selects into EVERY block (≈ 5 of 10 instructions per score element); the empty asm statements forbid that.
+                const int lim = (CAUSAL ? min(seqlen - 1, qpos) : seqlen - 1) - kv0;     // last live column of this row in the block
+#if defined(TEO_FA_DBG) && TEO_FA_DBG == 3      // timing decomposition builds only (results are garbage): no softmax at all
+                if (lim > -1000000) {
+                    tc_fence_before();
+                    mbar_arrive(&p_full[t]);
+                    continue;
+                }
+#endif
                 constexpr int NV = Cfg::REG_RESIDENT ? BN : 32;
                 uint32_t v[NV];
                 // chunk c (32 score columns) → registers, masked; REG_RESIDENT keeps all chunks live for the second pass
@@ -417,8 +459,8 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                     if (need_mask) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int kv = kv0 + c * 32 + i;
-                            if (kv >= seqlen || (CAUSAL && kv > qpos)) x[i] = 0xFF800000u;   // -inf
+                            if (c * 32 + i > lim) x[i] = 0xFF800000u;   // -inf: past the sequence end or (causal) past this row
+                            asm volatile("" : "+r"(x[i]));              // keeps this a branch (see above)
                         }
                     }
                 };
@@ -484,10 +526,19 @@ flash_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
+#if defined(TEO_FA_DBG) && TEO_FA_DBG == 1      // no MUFU
+                        const float p0 = fmaf(__uint_as_float(x[i]), g.scale_log2, neg_ms);
+                        const float p1 = fmaf(__uint_as_float(x[i + 1]), g.scale_log2, neg_ms);
+                        rs4[(i >> 1) & 3] += p0 + p1;
+                        pk[i >> 1] = pack_bf16x2(p0, p1);
+#elif defined(TEO_FA_DBG) && TEO_FA_DBG == 2    // no pass-2 arithmetic at all: TMEM traffic + pass 1 only
+                        pk[i >> 1] = x[i] ^ x[i + 1];
+#else
                         const float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), g.scale_log2, neg_ms));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), g.scale_log2, neg_ms));
                         rs4[(i >> 1) & 3] += p0 + p1;
                         pk[i >> 1] = pack_bf16x2(p0, p1);
+#endif
                     }
                     tmem_st_32x16(t_s + c * 16, pk);
                 };
