@@ -39,7 +39,9 @@ struct DmArgs {
     float* o_part;
     float* ml_part;
     int max_pages, len_bias, n_heads, n_splits, n_items;
-    int dbg_skip;               // measurement only (TEO_DEC_DBG_SKIP=1): consumers release pages without computing
+    int dbg_skip;               // measurement only (TEO_DEC_DBG_SKIP=1): consumers release pages without computing;
+                                // 2: additionally the page slices arrive as two linear 16 KiB bulk copies instead of four swizzled 8 KiB boxes
+    const bf16* kv;             // pool base (dbg_skip = 2 only)
     float scale_log2;
 };
 
@@ -114,10 +116,15 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tkv, const DmArgs g) 
                     const int krow = ((page * 2 + 0) * g.n_heads + head) * PAGE;
                     const int vrow = ((page * 2 + 1) * g.n_heads + head) * PAGE;
                     mbar_arrive_expect_tx(&full[st], DM_STAGE);
-                    tma_load_2d(dst, &tkv, &full[st], 0, krow);
-                    tma_load_2d(dst + DM_HALF, &tkv, &full[st], 64, krow);
-                    tma_load_2d(dst + DM_TILE, &tkv, &full[st], 0, vrow);
-                    tma_load_2d(dst + DM_TILE + DM_HALF, &tkv, &full[st], 64, vrow);
+                    if (g.dbg_skip == 2) {
+                        bulk_load_1d(dst, g.kv + static_cast<long long>(krow) * DM_HD, DM_TILE, &full[st]);
+                        bulk_load_1d(dst + DM_TILE, g.kv + static_cast<long long>(vrow) * DM_HD, DM_TILE, &full[st]);
+                    } else {
+                        tma_load_2d(dst, &tkv, &full[st], 0, krow);
+                        tma_load_2d(dst + DM_HALF, &tkv, &full[st], 64, krow);
+                        tma_load_2d(dst + DM_TILE, &tkv, &full[st], 0, vrow);
+                        tma_load_2d(dst + DM_TILE + DM_HALF, &tkv, &full[st], 64, vrow);
+                    }
                 }
                 __syncwarp();
             }
@@ -320,6 +327,7 @@ int launch_decode_attention_mma(teo_handle* h, const bf16* q, int ldq, const bf1
     g.scale_log2 = scale * 1.4426950408889634f;
     static const int dbg_skip = [] { const char* e = getenv("TEO_DEC_DBG_SKIP"); return e ? atoi(e) : 0; }();
     g.dbg_skip = dbg_skip;
+    g.kv = kv_pages;
     const int grid = std::min(g.n_items, h->num_sms * 3);
     TEO_CUDA(launch_kc(PDL_ATTN, decode_attn_mma_kernel, dim3(grid), dim3(DM_THREADS), DM_SMEM, stream, tkv, g));
     TEO_LAUNCH_CHECK("decode_attn_mma_kernel");

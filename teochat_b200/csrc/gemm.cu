@@ -100,8 +100,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* res_bar = tempty_bar + 2;                                 // [EPI_WARPS] residual tile landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+    uint64_t* res_bar = tempty_bar + 2;                                 // [EPI_WARPS][EPI_BUFS] residual tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + RES_BARS);
 
     pdl_trigger();                               // let the next kernel's launch + prologue overlap this one
     if (threadIdx.x == 0) {
@@ -131,7 +131,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], EPI_WARPS * 32);
         }
-        for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+        for (int s = 0; s < RES_BARS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -250,8 +250,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = ew & 3;                    // TMEM lane quadrant this warp may access (= warp % 4)
         const int hsel = ew >> 2;                // which column chunks of the tile this warp owns
         uint8_t* stg = staging + ew * 4096 * EPI_BUFS;
-        uint64_t* rbar = &res_bar[ew];
-        uint32_t rph = 0;
+        uint64_t* rbars = &res_bar[ew * EPI_BUFS];
+        uint32_t nchunk = 0;
         int as = 0;
         uint32_t aph = 0;
         Scheduler sc;
@@ -259,15 +259,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         WorkItem it;
         while (sc.next(g, it)) {
             const int m_blk = it.m_blk, n_blk = it.n_blk, split = it.slot;
-            mbar_wait(&tfull_bar[as], aph);
-            tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             if (!SK && g.tma_epi) {             // (the stream-K instantiation has no staging buffer and never runs this epilogue)
-                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, t_acc, m_blk, n_blk, stg, rbar, rph, lane, q, hsel, [&] {
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[as]);
-                });
+                staged_epilogue<BN, 1>(g, &tma_c, &tma_r, t_acc, 0u, m_blk, 0, n_blk, stg, rbars, nchunk, lane, q, hsel,
+                                       [&] {
+                                           mbar_wait(&tfull_bar[as], aph);
+                                           tc_fence_after();
+                                       },
+                                       [&] {
+                                           tc_fence_before();
+                                           mbar_arrive(&tempty_bar[as]);
+                                       });
             } else {
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
                 // ---- direct path: fp32 / split-K partial / transposed (swap-AB) outputs
                 const int m = m_blk * BM + q * 32 + lane;
                 const bool m_ok = m < g.M;

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -23,6 +25,8 @@ constexpr int EPI_WARPS = 8;
 #endif
 constexpr int EPI_BUFS = TEO_EPI_BUFS;
 constexpr int STAGING_BYTES = EPI_WARPS * 4096 * EPI_BUFS;
+constexpr int RES_BARS = EPI_WARPS * EPI_BUFS;       // one "residual tile landed" barrier per staging buffer
+constexpr int GEMM_BAR_BYTES = 512;                  // barrier area at the end of shared memory (≤ 16 + 4 + RES_BARS barriers + the TMEM slot)
 constexpr int GROUP_M = 16;     // rasterisation group (tiles along M sharing W tiles in L2)
 
 struct GemmArgs {
@@ -81,7 +85,7 @@ struct GemmCfg {
 #endif
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // power of two for BN ∈ {32,64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + GEMM_BAR_BYTES;
 };
 
 __device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
@@ -104,33 +108,42 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     return x;
 }
 
-// Staged epilogue of one 128 × BN accumulator tile (bf16 row-major output): this warp's 32 TMEM lanes × its 64-column
-// chunks → bias / activation / residual (residual tile fetched by TMA into the staging buffer) → bf16 → 128-byte-swizzled
-// staging → TMA store.  `release()` is called exactly once, right after this warp's last TMEM read of the tile (it frees
-// the accumulator stage for the MMA warp).  Shared by the single-CTA kernel (gemm.cu) and the CTA-pair kernel
-// (gemm_pair.cu), whose CTAs each own 128 rows of a 256-row tile.
-template <int BN, typename Release>
-__device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CUtensorMap* tma_c, const CUtensorMap* tma_r, uint32_t t_acc,
-                                                     int m_blk, int n_blk, uint8_t* stg_base, uint64_t* rbar, uint32_t& rph, int lane, int q,
-                                                     int hsel, Release release) {
-    // rph carries two counters: bit 0 = phase of the residual barrier, bits 1.. = chunks staged so far (selects the staging buffer)
-    auto next_buf = [&]() -> uint8_t* {
-        uint8_t* b = stg_base + ((rph >> 1) % EPI_BUFS) * 4096;
-        rph += 2;
-        return b;
-    };
+// Staged epilogue of the MT row sub-tiles (128 × BN accumulators each) of one output tile, bf16 row-major output: this warp's 32 TMEM
+// lanes × its 64-column chunks → bias / activation / residual → bf16 → 128-byte-swizzled staging → TMA store.  Shared by the
+// single-CTA kernel (gemm.cu, MT = 1) and the CTA-pair kernel (gemm_pair.cu, whose CTAs each own 128 rows of every 256-row sub-tile).
+//   t_acc + sub·acc_stride   TMEM address of sub-tile `sub` (lane quadrant included);  its rows are block m_blk0 + sub·m_stride
+//   stg_base / rbars         this warp's EPI_BUFS staging buffers (4 KiB each) and their "residual landed" barriers
+//   nchunk                   chunks this warp has staged since the kernel started: selects buffer and barrier phase
+//   wait_full()              waits for the accumulators (called once, AFTER the first residual chunk has been requested)
+//   release()                called exactly once, right after this warp's last TMEM read of the tile
+// The residual tile of a chunk is fetched by TMA into the staging buffer the chunk is then converted in.  With two buffers the
+// request for chunk i+1 is issued while chunk i is read from TMEM and converted, and the first chunk of a tile is requested before
+// the accumulators are even waited for — the L2 round trip of the residual used to be paid once per chunk, un-overlapped, which
+// is what made the epilogue of the 512-row pair tiles (not overlapped by a second accumulator stage) cost ≈ 12 k cycles per tile.
+template <int BN, int MT, typename WaitFull, typename Release>
+__device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtensorMap* tma_c, const CUtensorMap* tma_r, uint32_t t_acc,
+                                                uint32_t acc_stride, int m_blk0, int m_stride, int n_blk, uint8_t* stg_base, uint64_t* rbars,
+                                                uint32_t& nchunk, int lane, int q, int hsel, WaitFull wait_full, Release release) {
     if (g.act == TEO_ACT_SWIGLU_PAIRS) {
         // ---- SwiGLU fused into the gate/up projection: the weight rows come interleaved in blocks of 32
         // (…| gate 32 | up 32 |…), so accumulator columns [c, c+32) and [c+32, c+64) are the gate and the up
         // projection of the SAME 32 outputs.  A warp turns two such 64-column chunks into one 64-column
         // output chunk — bf16(silu(bf16(g)) · bf16(u)), the rounding points of the unfused chain — and
         // stores it with the usual TMA box; C has N/2 columns.
-        const int row0 = m_blk * BM + q * 32;
+        constexpr int CPW = (BN / 128 + 1) / 2;                       // output chunks per warp and sub-tile
+        int cv = 0;
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) cv += (2 * (n_blk * (BN / 2) + (hsel + 2 * i) * 64) < g.N && hsel + 2 * i < BN / 128) ? 1 : 0;
+        const int m = MT * cv;
+        wait_full();
+        if (m == 0) release();                                         // this warp owned no chunk of the tile
 #pragma unroll 1
-        for (int oc = hsel; oc < BN / 128; oc += 2) {
+        for (int i = 0; i < m; ++i) {
+            const int sub = i / cv, oc = hsel + 2 * (i - sub * cv);
+            const int row0 = (m_blk0 + sub * m_stride) * BM + q * 32;
             const int n_out0 = n_blk * (BN / 2) + oc * 64;
-            if (2 * n_out0 >= g.N) break;              // warp-uniform
-            uint8_t* stg = next_buf();
+            uint8_t* stg = stg_base + (nchunk % EPI_BUFS) * 4096;
+            ++nchunk;
             if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this staging buffer has drained it
             __syncwarp();
 #pragma unroll
@@ -138,16 +151,14 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
                 const int col = oc * 128 + hc * 64;
                 uint32_t vg[32], vu[32];
                 if (n_blk * BN + col < g.N) {
-                    tmem_ld_32x32(t_acc + col, vg);
-                    tmem_ld_32x32(t_acc + col + 32, vu);
+                    tmem_ld_32x32(t_acc + sub * acc_stride + col, vg);
+                    tmem_ld_32x32(t_acc + sub * acc_stride + col + 32, vu);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) vg[j] = vu[j] = 0u;
                 }
-                if (hc == 1 && (oc + 2 >= BN / 128 || 2 * (n_out0 + 128) >= g.N)) {   // last chunk of this warp
-                    release();
-                }
+                if (hc == 1 && i == m - 1) release();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float x[8];
@@ -155,7 +166,7 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
                     for (int j = 0; j < 8; ++j) {
                         const float gg = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vg[c * 8 + j])));
                         const float uu = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vu[c * 8 + j])));
-                        x[j] = (gg / (1.0f + expf(-gg))) * uu;
+                        x[j] = silu_mul_fast(gg, uu);
                     }
                     const int cc = hc * 4 + c;
                     *reinterpret_cast<uint4*>(stg + lane * 128 + ((cc ^ (lane & 7)) << 4)) =
@@ -169,114 +180,148 @@ __device__ __forceinline__ void staged_epilogue_tile(const GemmArgs& g, const CU
                 tma_store_commit();
             }
         }
-        if (hsel >= BN / 128 || 2 * (n_blk * (BN / 2) + hsel * 64) >= g.N) {   // this warp owned no chunk of the tile
-            release();
-        }
-    } else {
-        // ---- staged path: 64-column chunks → swizzled smem → TMA store
-        const int row0 = m_blk * BM + q * 32;
-        const bool has_res = g.residual != nullptr;
-        // folded LayerNorm: this thread's row statistics (fixed summation order over the producer's slots → deterministic)
-        float ln_mu = 0.f, ln_rstd = 1.f;
-        if (g.ln_stats != nullptr && row0 + lane < g.M) {
-            const float* st = g.ln_stats + static_cast<long long>(row0 + lane) * g.ln_slots * 2;
-            float s1 = 0.f, s2 = 0.f;
-            for (int i = 0; i < g.ln_slots; ++i) { s1 += st[2 * i]; s2 += st[2 * i + 1]; }
-            ln_mu = s1 * g.ln_inv_d;
-            ln_rstd = rsqrtf(fmaxf(s2 * g.ln_inv_d - ln_mu * ln_mu, 0.f) + g.ln_eps);
-        }
-        float st1 = 0.f, st2 = 0.f;            // Σ, Σ² of the bf16 values this warp writes for its row
+        return;
+    }
+    // ---- staged path: 64-column chunks → swizzled smem → TMA store
+    constexpr int CPW = (BN / 64 + 1) / 2;                            // chunks per warp and sub-tile
+    constexpr bool PIPE = EPI_BUFS >= 2;                               // residual of chunk i+1 requested while chunk i is converted
+    const bool has_res = g.residual != nullptr;
+    int cv = 0;
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) cv += (n_blk * BN + (hsel + 2 * i) * 64 < g.N && hsel + 2 * i < BN / 64) ? 1 : 0;
+    const int m = MT * cv;
+    auto chunk_at = [&](int i, int& sub, int& n0, int& row0) {
+        sub = i / cv;
+        n0 = n_blk * BN + (hsel + 2 * (i - sub * cv)) * 64;
+        row0 = (m_blk0 + sub * m_stride) * BM + q * 32;
+    };
+    // lane 0: request the residual tile of chunk i (staging buffer / barrier of chunk number `no`); `pending` = TMA stores that may
+    // still be reading their buffers — the one that last used THIS buffer must not be among them
+    auto request_res = [&](int i, uint32_t no, auto pending) {
+        int sub, n0, row0;
+        chunk_at(i, sub, n0, row0);
+        tma_store_wait_read<decltype(pending)::value>();
+        mbar_arrive_expect_tx(&rbars[no % EPI_BUFS], 4096);
+        tma_load_2d(stg_base + (no % EPI_BUFS) * 4096, tma_r, &rbars[no % EPI_BUFS], n0, row0);
+    };
+    if (has_res && m > 0 && lane == 0) request_res(0, nchunk, std::integral_constant<int, EPI_BUFS - 1>{});
+    wait_full();
+    if (m == 0) release();                                             // this warp owned no chunk of the tile
+    float ln_mu = 0.f, ln_rstd = 1.f;
+    float st1 = 0.f, st2 = 0.f;            // Σ, Σ² of the bf16 values this warp writes for its row (current sub-tile)
 #pragma unroll 1
-        for (int cj = hsel; cj < BN / 64; cj += 2) {
-            const int n0 = n_blk * BN + cj * 64;
-            if (n0 >= g.N) break;                      // warp-uniform
-            uint8_t* stg = next_buf();
-            if (lane == 0) {
+    for (int i = 0; i < m; ++i) {
+        int sub, n0, row0;
+        chunk_at(i, sub, n0, row0);
+        const bool sub_first = (i - sub * cv) == 0, sub_last = (i - sub * cv) == cv - 1;
+        const uint32_t no = nchunk++;
+        uint8_t* stg = stg_base + (no % EPI_BUFS) * 4096;
+        if (sub_first && g.ln_stats != nullptr) {
+            // folded LayerNorm: this thread's row statistics (fixed summation order over the producer's slots → deterministic)
+            ln_mu = 0.f; ln_rstd = 1.f;
+            if (row0 + lane < g.M) {
+                const float* st = g.ln_stats + static_cast<long long>(row0 + lane) * g.ln_slots * 2;
+                float s1 = 0.f, s2 = 0.f;
+                for (int k = 0; k < g.ln_slots; ++k) { s1 += st[2 * k]; s2 += st[2 * k + 1]; }
+                ln_mu = s1 * g.ln_inv_d;
+                ln_rstd = rsqrtf(fmaxf(s2 * g.ln_inv_d - ln_mu * ln_mu, 0.f) + g.ln_eps);
+            }
+        }
+        if (lane == 0) {
+            if (!has_res) {
                 tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this staging buffer has drained it
-                if (has_res) {
-                    mbar_arrive_expect_tx(rbar, 4096);
-                    tma_load_2d(stg, tma_r, rbar, n0, row0);
-                }
+            } else if (!PIPE && i > 0) {
+                request_res(i, no, std::integral_constant<int, EPI_BUFS - 1>{});
             }
-            __syncwarp();
-            // The chunk's 64 bias values first (8 × 16 bytes, the same addresses in every lane): issued together, their L1 / L2
-            // latency overlaps the TMEM read and the residual tile's arrival.  Loaded one group at a time inside the loop below they
-            // were eight dependent round trips per chunk — on the K = 1024 GEMMs of the ViT (short main loop, every linear has a
-            // bias) that made the epilogue, not the tensor pipe, the critical path.
-            uint4 bvec[8];
-            if (g.bias != nullptr && g.ln_stats == nullptr) {
+        }
+        __syncwarp();
+        // The chunk's 64 bias values first (8 × 16 bytes, the same addresses in every lane): issued together, their L1 / L2
+        // latency overlaps the TMEM read and the residual tile's arrival.  Loaded one group at a time inside the loop below they
+        // were eight dependent round trips per chunk — on the K = 1024 GEMMs of the ViT (short main loop, every linear has a
+        // bias) that made the epilogue, not the tensor pipe, the critical path.
+        uint4 bvec[8];
+        if (g.bias != nullptr && g.ln_stats == nullptr) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    bvec[c] = (n0 + c * 8 < g.N) ? *reinterpret_cast<const uint4*>(g.bias + n0 + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+            for (int c = 0; c < 8; ++c)
+                bvec[c] = (n0 + c * 8 < g.N) ? *reinterpret_cast<const uint4*>(g.bias + n0 + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t v0[32], v1[32];
+        const uint32_t t_chunk = t_acc + sub * acc_stride + static_cast<uint32_t>(n0 - n_blk * BN);
+        tmem_ld_32x32(t_chunk, v0);
+        tmem_ld_32x32(t_chunk + 32, v1);
+        if (PIPE && has_res && i + 1 < m && lane == 0)      // the next chunk's residual: its buffer was last read by the store of chunk no − 1
+            request_res(i + 1, no + 1, std::integral_constant<int, (EPI_BUFS >= 2 ? EPI_BUFS - 2 : 0)>{});
+        __syncwarp();
+        tmem_ld_wait();
+        if (i == m - 1) release();                          // last chunk of this warp: the accumulators are free
+        if (has_res) mbar_wait(&rbars[no % EPI_BUFS], (no / EPI_BUFS) & 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
+            const int n = n0 + c * 8;
+            if (g.ln_stats != nullptr && n < g.N) {
+                const float4 c0 = *reinterpret_cast<const float4*>(g.ln_c + n), c1 = *reinterpret_cast<const float4*>(g.ln_c + n + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(g.ln_bias + n), b1 = *reinterpret_cast<const float4*>(g.ln_bias + n + 4);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = fmaf(ln_rstd, x[j] - ln_mu * cc[j], bb[j]);
+            } else if (g.bias && n < g.N) {
+                const uint4 bv = bvec[c];
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
             }
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(t_acc + cj * 64, v0);
-            tmem_ld_32x32(t_acc + cj * 64 + 32, v1);
-            tmem_ld_wait();
-            if (cj + 2 >= BN / 64 || n0 + 128 >= g.N) {   // last chunk of this warp: accumulator stage is free
-                release();
+            if (g.act != TEO_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
             }
+            uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
             if (has_res) {
-                mbar_wait(rbar, rph & 1);
-                rph ^= 1;
+                const uint4 rv = *slot;
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
             }
+            const uint4 packed = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                            pack_bf16x2(x[6], x[7]));
+            *slot = packed;
+            if (g.stats_out != nullptr) {          // statistics of the values AS STORED (bf16), columns past N hold zeros
+                const uint32_t pw[4] = {packed.x, packed.y, packed.z, packed.w};
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
-                const int n = n0 + c * 8;
-                if (g.ln_stats != nullptr && n < g.N) {
-                    const float4 c0 = *reinterpret_cast<const float4*>(g.ln_c + n), c1 = *reinterpret_cast<const float4*>(g.ln_c + n + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(g.ln_bias + n), b1 = *reinterpret_cast<const float4*>(g.ln_bias + n + 4);
-                    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = fmaf(ln_rstd, x[j] - ln_mu * cc[j], bb[j]);
-                } else if (g.bias && n < g.N) {
-                    const uint4 bv = bvec[c];
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+                for (int j = 0; j < 4; ++j) {
+                    const float lo = bf16_lo(pw[j]), hi = bf16_hi(pw[j]);
+                    st1 += lo + hi;
+                    st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
                 }
-                if (g.act != TEO_ACT_NONE) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], g.act);
-                }
-                uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
-                if (has_res) {
-                    const uint4 rv = *slot;
-                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
-                }
-                const uint4 packed = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                                pack_bf16x2(x[6], x[7]));
-                *slot = packed;
-                if (g.stats_out != nullptr) {          // statistics of the values AS STORED (bf16), columns past N hold zeros
-                    const uint32_t pw[4] = {packed.x, packed.y, packed.z, packed.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float lo = bf16_lo(pw[j]), hi = bf16_hi(pw[j]);
-                        st1 += lo + hi;
-                        st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
-                    }
-                }
-            }
-            fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(tma_c, stg, n0, row0);
-                tma_store_commit();
             }
         }
-        if (hsel >= BN / 64 || n_blk * BN + hsel * 64 >= g.N) {   // this warp owned no chunk of the tile
-            release();
+        fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tma_c, stg, n0, row0);
+            tma_store_commit();
         }
-        if (g.stats_out != nullptr && row0 + lane < g.M) {         // (zeros from a warp that owned no chunk: the consumer sums all slots)
-            float* so = g.stats_out + (static_cast<long long>(row0 + lane) * g.stats_slots + n_blk * 2 + hsel) * 2;
-            so[0] = st1;
-            so[1] = st2;
+        if (sub_last && g.stats_out != nullptr) {
+            if (row0 + lane < g.M) {
+                float* so = g.stats_out + (static_cast<long long>(row0 + lane) * g.stats_slots + n_blk * 2 + hsel) * 2;
+                so[0] = st1;
+                so[1] = st2;
+            }
+            st1 = st2 = 0.f;
+        }
+    }
+    if (m == 0 && g.stats_out != nullptr) {        // zeros from a warp that owned no chunk: the consumer sums all slots
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+            const int row0 = (m_blk0 + sub * m_stride) * BM + q * 32;
+            if (row0 + lane < g.M) {
+                float* so = g.stats_out + (static_cast<long long>(row0 + lane) * g.stats_slots + n_blk * 2 + hsel) * 2;
+                so[0] = 0.f;
+                so[1] = 0.f;
+            }
         }
     }
 }

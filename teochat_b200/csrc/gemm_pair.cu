@@ -13,7 +13,7 @@
 //   warp 1      MMA issuer (leader only): waits full → 4 UMMAs per k-block → tcgen05.commit …multicast frees the ring
 //               slot in BOTH CTAs; after the last k-block a multicast commit publishes the accumulator stage to both
 //   warp 2      TMEM allocator (cta_group::2 alloc / dealloc, the same warp in both CTAs)
-//   warps 4-11  epilogue (both CTAs, each on its own 128 rows): staged_epilogue_tile; the accumulator stage is released
+//   warps 4-11  epilogue (both CTAs, each on its own 128 rows): staged_epilogue; the accumulator stage is released
 //               by arriving on the leader's tempty barrier (remote arrive from the peer)
 // Persistent: pair p walks tiles p, p + pairs, … rasterised in groups of 16 tile rows (4096 rows of A stay in L2 while W
 // streams).  Selected by launch_gemm (gemm.cu) for M > 128, N ≥ 256, bf16 output; TEO_GEMM_PAIR=0 keeps the single-CTA
@@ -41,7 +41,7 @@ template <int MT>
 struct PairCfg {
     static constexpr int STAGE_BYTES = MT * A_STAGE_BYTES + PAIR_HALF_B_BYTES;    // 32 / 48 KiB
     static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;          // 6 / 4 with one staging buffer per warp, 5 / 3 with two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + GEMM_BAR_BYTES;
 };
 
 struct PairTile {
@@ -95,7 +95,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;                                          // used in the leader only
     uint64_t* res_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + RES_BARS);
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5;
@@ -122,7 +122,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], 2 * EPI_WARPS * 32);       // the epilogue threads of both CTAs
         }
-        for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+        for (int s = 0; s < RES_BARS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair<PAIR_TMEM_COLS>(tmem_slot);
@@ -204,28 +204,27 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int q = ew & 3;
         const int hsel = ew >> 2;
         uint8_t* stg = staging + ew * 4096 * EPI_BUFS;
-        uint64_t* rbar = &res_bar[ew];
-        uint32_t rph = 0;
+        uint64_t* rbars = &res_bar[ew * EPI_BUFS];
+        uint32_t nchunk = 0;
         int as = 0;
         uint32_t aph = 0;
         for (int unit = pair; unit < units; unit += n_pairs) {
             const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
-            mbar_wait(&tfull_bar[as], aph);
-            tc_fence_after();
             const uint32_t lanes = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-            if constexpr (MT == 1) {
-                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes + as * BN, t.m2 * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
-                    tc_fence_before();
-                    mbar_arrive_leader(&tempty_bar[as]);
-                });
-            } else {
-                // the two row sub-tiles one after the other; the accumulators are handed back after the LAST read of the second
-                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes, (t.m2 * MT) * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [] {});
-                staged_epilogue_tile<BN>(g, &tma_c, &tma_r, lanes + BN, (t.m2 * MT + 1) * 2 + rank, t.n_blk, stg, rbar, rph, lane, q, hsel, [&] {
-                    tc_fence_before();
-                    mbar_arrive_leader(&tempty_bar[as]);
-                });
-            }
+            // MT = 1: this accumulator stage's 128 x 256 tile; MT = 2: the two row sub-tiles one after the other (accumulators at columns
+            // 0 and 256), handed back after the LAST read of the second.  The residual of the first chunk is requested before the wait.
+            staged_epilogue<BN, MT>(g, &tma_c, &tma_r, lanes + (MT == 1 ? as * BN : 0), static_cast<uint32_t>(BN), (t.m2 * MT) * 2 + rank, 2, t.n_blk,
+                                    stg, rbars, nchunk, lane, q, hsel,
+                                    [&] {
+                                        // (One polling warp + bar.sync for the other seven, with a suspend-time hint on the wait, was built and
+                                        // A/B-measured: 3/4 fewer instructions executed, no change in sustained rate — scripts/gpu_r02_epi6.sh.)
+                                        mbar_wait(&tfull_bar[as], aph);
+                                        tc_fence_after();
+                                    },
+                                    [&] {
+                                        tc_fence_before();
+                                        mbar_arrive_leader(&tempty_bar[as]);
+                                    });
             if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
         }
         if (lane == 0) tma_store_wait_all<0>();
@@ -268,10 +267,12 @@ int launch_gemm_pair(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& tb
         const char* e = getenv("TEO_PAIR_MT");
         return e ? atoi(e) : 0;
     }();
-    // Rule: MT = 2 only where the un-overlapped epilogue of two sub-tiles (≈ 12 k cycles) is small against the main loop — the down
-    // projection (K = 11008: −7 % stand-alone); at K = 4096 the gate/up (SwiGLU) and o (residual) GEMMs lose what the operand
-    // traffic gains (same-box A/B, scripts/gpu_r02_mt.sh: prefill 816.8 → 807.9 ms with MT = 2 on every K ≥ 2048 GEMM).
-    const int mt = env_mt == 1 || env_mt == 2 ? env_mt : ((g.K >= (env_mt >= 1024 ? env_mt : 8192) && g.M >= 8192) ? 2 : 1);
+    // Rule: MT = 2 wherever the un-overlapped epilogue of the two sub-tiles is small against the main loop: K >= 4096, i.e. all four
+    // prefill GEMMs.  (Round 2, first version: only the down projection, K = 11008, gained — the residual epilogue paid one L2 round
+    // trip per chunk and the SwiGLU epilogue ~20 instructions per output; with the residual prefetched a chunk ahead and
+    // ex2/rcp.approx SwiGLU (gemm_common.cuh) the same-box A/B reads prefill 786 -> 766 ms for K >= 4096 against K >= 8192,
+    // scripts/gpu_r02_epi3.sh.)  At K = 1024 (ViT) the 512-row tiles lose 10-30 %: TEO_PAIR_MT=1024 shows it.
+    const int mt = env_mt == 1 || env_mt == 2 ? env_mt : ((g.K >= (env_mt >= 1024 ? env_mt : 4096) && g.M >= 8192) ? 2 : 1);
     const int units = ((g.M + mt * 2 * BM - 1) / (mt * 2 * BM)) * ((g.N + PAIR_BN - 1) / PAIR_BN);
     const int pairs = std::max(1, std::min(units, h->num_sms / 2));
     // Rasterisation group: W is re-read from HBM once per group of tile rows, so bigger groups mean less DRAM traffic (and

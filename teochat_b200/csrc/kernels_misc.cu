@@ -260,7 +260,7 @@ __global__ void swiglu_kernel(const bf16* __restrict__ gate_up, bf16* __restrict
         load8(gate_up + r * 2 * inter + gc, g);
         load8(gate_up + r * 2 * inter + gc + up_off, u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (g[j] / (1.0f + expf(-g[j]))) * u[j];
+        for (int j = 0; j < 8; ++j) y[j] = silu_mul_fast(g[j], u[j]);
         store8(out + r * inter + c, y);
     }
 }

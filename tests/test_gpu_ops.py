@@ -42,7 +42,7 @@ GEMM_SHAPES = [
     (200, 128, 256), (130, 64, 128), (513, 328, 200),
     (1, 4096, 4096), (5, 512, 256), (32, 12288, 4096), (32, 4096, 11008), (64, 1024, 512), (100, 32000, 512), (17, 256, 64),
     # long K over many rows: the 512-row pair tiles (gemm_pair_kernel<2>), M not a multiple of 512 / 256 / 128
-    (8200, 768, 2048), (8977, 512, 4096),
+    (8200, 768, 4096), (8977, 512, 4096), (8200, 768, 2048),
 ]
 
 
@@ -111,10 +111,11 @@ def test_gemm_swiglu_pairs_epilogue(teo, M, I, K, blocked):
 
 
 def test_gemm_512_row_pair_tiles_with_epilogues(teo):
-    """gemm_pair_kernel<2> (M >= 8192, K >= 2048: two 256-row sub-tiles per pair tile, one shared W k-block) with the epilogues the
-    prefill uses on it: residual (o / down), SwiGLU pairs (gate/up), bias + activation."""
+    """gemm_pair_kernel<2> (M >= 8192, K >= 4096: two 256-row sub-tiles per pair tile, one shared W k-block) with the epilogues the
+    prefill uses on it: residual (o / down; the residual tiles are prefetched a chunk ahead, the first one before the accumulators
+    are complete), SwiGLU pairs (gate/up), bias + activation."""
     lib, h = teo
-    M, N, K = 8300, 1024, 2048
+    M, N, K = 8300, 1024, 4096
     A, W = bf(rnd(M, K, seed=3)), bf(rnd(N, K, scale=K ** -0.5, seed=4))
     bias, res = bf(rnd(N, scale=0.1, seed=5)), bf(rnd(M, N, seed=6))
     ref = A.float() @ W.float().t()
