@@ -9,6 +9,10 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#ifndef EPI_STAMP        // gemm_pair.cu's development build (TEO_PAIR_TRACE) stamps clock64 at these points of a tile's first chunk
+#define EPI_STAMP(slot) do { } while (0)
+#endif
+
 namespace teo {
 
 constexpr int BM = 128;         // UMMA M
@@ -108,6 +112,51 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     return x;
 }
 
+// One 64-column chunk: 2 × 32 accumulator columns of this thread's row → (+ bias) → activation → (+ residual, read from the
+// staging buffer the TMA load put it in) → bf16 → 128-byte-swizzled staging row.  Compile-time specialised: written as ONE loop
+// with run-time tests of g.bias / g.act / g.ln_stats / g.stats_out / g.residual the chunk body compiled to ≈ 2 900 SASS
+// instructions (64 inlined erff expansions, the folded-LayerNorm loads, the statistics, …), 46 KB of code that eight warps walked
+// through taking branches around almost all of it — instruction fetch, not arithmetic, made a chunk cost ≈ 2.2 k cycles
+// (clock64 stamps inside the epilogue, profiles/r02_pair_epilogue.txt).  Each specialisation is ≈ 200 instructions.
+template <int ACT, bool HAS_BIAS, bool HAS_RES>
+__device__ __forceinline__ void convert_chunk(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const uint4 (&bvec)[8], uint8_t* stg,
+                                              int lane) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
+        if constexpr (HAS_BIAS) {              // (columns past N carry zeros in bvec; what is computed for them is clipped by the TMA store)
+            const uint32_t bw[4] = {bvec[c].x, bvec[c].y, bvec[c].z, bvec[c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(bw[j]); x[2 * j + 1] += bf16_hi(bw[j]); }
+        }
+        if constexpr (ACT != TEO_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = apply_act(x[j], ACT);
+        }
+        uint4* slot = reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4));
+        if constexpr (HAS_RES) {
+            const uint4 rv = *slot;
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x[2 * j] += bf16_lo(rw[j]); x[2 * j + 1] += bf16_hi(rw[j]); }
+        }
+        *slot = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    }
+}
+template <int ACT>
+__device__ __forceinline__ void convert_chunk_act(bool has_bias, bool has_res, const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                                  const uint4 (&bvec)[8], uint8_t* stg, int lane) {
+    if (has_bias) {
+        if (has_res) convert_chunk<ACT, true, true>(v0, v1, bvec, stg, lane);
+        else convert_chunk<ACT, true, false>(v0, v1, bvec, stg, lane);
+    } else {
+        if (has_res) convert_chunk<ACT, false, true>(v0, v1, bvec, stg, lane);
+        else convert_chunk<ACT, false, false>(v0, v1, bvec, stg, lane);
+    }
+}
+
 // Staged epilogue of the MT row sub-tiles (128 × BN accumulators each) of one output tile, bf16 row-major output: this warp's 32 TMEM
 // lanes × its 64-column chunks → bias / activation / residual → bf16 → 128-byte-swizzled staging → TMA store.  Shared by the
 // single-CTA kernel (gemm.cu, MT = 1) and the CTA-pair kernel (gemm_pair.cu, whose CTAs each own 128 rows of every 256-row sub-tile).
@@ -186,6 +235,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtenso
     constexpr int CPW = (BN / 64 + 1) / 2;                            // chunks per warp and sub-tile
     constexpr bool PIPE = EPI_BUFS >= 2;                               // residual of chunk i+1 requested while chunk i is converted
     const bool has_res = g.residual != nullptr;
+    const bool generic = g.ln_stats != nullptr || g.stats_out != nullptr;      // folded LayerNorm / row statistics: the one-loop-does-all path
     int cv = 0;
 #pragma unroll
     for (int i = 0; i < CPW; ++i) cv += (n_blk * BN + (hsel + 2 * i) * 64 < g.N && hsel + 2 * i < BN / 64) ? 1 : 0;
@@ -227,6 +277,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtenso
                 ln_rstd = rsqrtf(fmaxf(s2 * g.ln_inv_d - ln_mu * ln_mu, 0.f) + g.ln_eps);
             }
         }
+        if (i == 0) EPI_STAMP(10);
         if (lane == 0) {
             if (!has_res) {
                 tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this staging buffer has drained it
@@ -235,6 +286,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtenso
             }
         }
         __syncwarp();
+        if (i == 0) EPI_STAMP(11);
         // The chunk's 64 bias values first (8 × 16 bytes, the same addresses in every lane): issued together, their L1 / L2
         // latency overlaps the TMEM read and the residual tile's arrival.  Loaded one group at a time inside the loop below they
         // were eight dependent round trips per chunk — on the K = 1024 GEMMs of the ViT (short main loop, every linear has a
@@ -253,10 +305,19 @@ __device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtenso
             request_res(i + 1, no + 1, std::integral_constant<int, (EPI_BUFS >= 2 ? EPI_BUFS - 2 : 0)>{});
         __syncwarp();
         tmem_ld_wait();
+        if (i == 0) EPI_STAMP(12);
         if (i == m - 1) release();                          // last chunk of this warp: the accumulators are free
         if (has_res) mbar_wait(&rbars[no % EPI_BUFS], (no / EPI_BUFS) & 1);
+        if (i == 0) EPI_STAMP(13);
+        if (!generic) {
+            // the specialisations (warp-uniform dispatch, once per chunk)
+            const bool hb = g.bias != nullptr;
+            if (g.act == TEO_ACT_NONE) convert_chunk_act<TEO_ACT_NONE>(hb, has_res, v0, v1, bvec, stg, lane);
+            else if (g.act == TEO_ACT_QUICK_GELU) convert_chunk_act<TEO_ACT_QUICK_GELU>(hb, has_res, v0, v1, bvec, stg, lane);
+            else convert_chunk_act<TEO_ACT_GELU>(hb, has_res, v0, v1, bvec, stg, lane);
+        } else
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {              // eight 16-byte groups of 8 columns
+        for (int c = 0; c < 8; ++c) {              // generic path (folded LayerNorm / row statistics): eight 16-byte groups of 8 columns
             float x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(c < 4 ? v0[c * 8 + j] : v1[(c - 4) * 8 + j]);
@@ -298,8 +359,10 @@ __device__ __forceinline__ void staged_epilogue(const GemmArgs& g, const CUtenso
                 }
             }
         }
+        if (i == 0) EPI_STAMP(14);
         fence_proxy_async();                       // generic-proxy writes → visible to the TMA engine
         __syncwarp();
+        if (i == 0) EPI_STAMP(15);
         if (lane == 0) {
             tma_store_2d(tma_c, stg, n0, row0);
             tma_store_commit();

@@ -23,6 +23,19 @@
 #include <algorithm>
 
 #include "common.h"
+#ifdef TEO_PAIR_TRACE
+// (development build) stamps inside the shared epilogue: warp 4 / lane 0 of this translation unit's kernel only
+namespace teo {
+__device__ unsigned long long* g_pair_trace = nullptr;
+__device__ int g_pair_trace_tiles = 0;
+__device__ int g_pair_trace_tile_no[148];          // tile the epilogue of each CTA is working on (for the stamps inside staged_epilogue)
+}  // namespace teo
+#define EPI_STAMP(slot)                                                                                                                  \
+    do {                                                                                                                                 \
+        if (teo::g_pair_trace != nullptr && (threadIdx.x == 128) && teo::g_pair_trace_tile_no[blockIdx.x] < teo::g_pair_trace_tiles)                    \
+            teo::g_pair_trace[(static_cast<long long>(blockIdx.x) * teo::g_pair_trace_tiles + teo::g_pair_trace_tile_no[blockIdx.x]) * 16 + (slot)] = clock64(); \
+    } while (0)
+#endif
 #include "gemm_common.cuh"
 #include "ptx.cuh"
 
@@ -43,6 +56,19 @@ struct PairCfg {
     static constexpr int STAGES = (229376 - STAGING_BYTES) / STAGE_BYTES;          // 6 / 4 with one staging buffer per warp, 5 / 3 with two
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + GEMM_BAR_BYTES;
 };
+
+#ifdef TEO_PAIR_TRACE
+// Development build only (build.build_variant("pairtrace", ["TEO_PAIR_TRACE"]), tools/pair_trace.py): clock64 stamps per tile of every CTA,
+// u64 [n_ctas][max_tiles][16]: 0 issuer past tempty · 1 issuer has k-block 0 · 2 issuer committed tfull · 3 epilogue saw tfull ·
+// 4 epilogue released the accumulators · 5 epilogue done · 6 producer issued k-block 0 · 7 producer issued the last k-block · 8 / 9 producer saw the ring slot of k-block 0 / STAGES free again
+#define PAIR_STAMP(tile, slot)                                                                                         \
+    do {                                                                                                               \
+        if (g_pair_trace != nullptr && (tile) < g_pair_trace_tiles)                                                    \
+            g_pair_trace[(static_cast<long long>(blockIdx.x) * g_pair_trace_tiles + (tile)) * 16 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define PAIR_STAMP(tile, slot) do { } while (0)
+#endif
 
 struct PairTile {
     int m2, n_blk;
@@ -144,10 +170,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t h_stream = (g.l2_hint == 1 || g.l2_hint == 3) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
             const uint64_t hint_a = g.raster == 0 ? h_stay : h_stream;
             const uint64_t hint_w = g.raster == 0 ? h_stream : h_stay;
-            for (int unit = pair; unit < units; unit += n_pairs) {
+            int tile_no = 0;
+            for (int unit = pair; unit < units; unit += n_pairs, ++tile_no) {
                 const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (kb == 0) PAIR_STAMP(tile_no, 6);
+                    if (kb == total_kb - 1) PAIR_STAMP(tile_no, 7);
+                    if (kb == STAGES) PAIR_STAMP(tile_no, 8);
+                    if (kb == 2 * STAGES) PAIR_STAMP(tile_no, 9);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * PairCfg<MT>::STAGE_BYTES);
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub) {             // this CTA's 128 rows of every 256-row sub-tile
@@ -174,13 +205,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int unit = pair; unit < units; unit += n_pairs) {
+            int tile_no = 0;
+            for (int unit = pair; unit < units; unit += n_pairs, ++tile_no) {
                 mbar_wait(&tempty_bar[as], aph ^ 1);             // both CTAs' epilogues have drained this accumulator stage
                 tc_fence_after();
+                PAIR_STAMP(tile_no, 0);
                 const uint32_t d_tmem = tmem_base + (MT == 1 ? as * BN : 0);
                 for (int kb = 0; kb < total_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);                 // both CTAs' halves of the stage have landed
                     tc_fence_after();
+                    if (kb == 0) PAIR_STAMP(tile_no, 1);
                     const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + s * PAIR_HALF_B_BYTES));
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub) {         // MT = 2: the W k-block feeds both row sub-tiles (accumulators sub · 256)
@@ -190,7 +224,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             umma_bf16_pair(d_tmem + sub * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit_pair(&empty_bar[s], 3);          // frees the ring slot in both CTAs when the MMAs retire
-                    if (kb == total_kb - 1) umma_commit_pair(&tfull_bar[as], 3);
+                    if (kb == total_kb - 1) {
+                        umma_commit_pair(&tfull_bar[as], 3);
+                        PAIR_STAMP(tile_no, 2);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
@@ -208,8 +245,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t nchunk = 0;
         int as = 0;
         uint32_t aph = 0;
-        for (int unit = pair; unit < units; unit += n_pairs) {
+        int tile_no = 0;
+        for (int unit = pair; unit < units; unit += n_pairs, ++tile_no) {
             const PairTile t = pair_tile(unit, num_m2, num_n, g.sk_q, g.group_n, g.raster);
+#ifdef TEO_PAIR_TRACE
+            if (threadIdx.x == 128) g_pair_trace_tile_no[blockIdx.x] = tile_no;
+#endif
             const uint32_t lanes = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
             // MT = 1: this accumulator stage's 128 x 256 tile; MT = 2: the two row sub-tiles one after the other (accumulators at columns
             // 0 and 256), handed back after the LAST read of the second.  The residual of the first chunk is requested before the wait.
@@ -220,11 +261,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                         // A/B-measured: 3/4 fewer instructions executed, no change in sustained rate — scripts/gpu_r02_epi6.sh.)
                                         mbar_wait(&tfull_bar[as], aph);
                                         tc_fence_after();
+                                        if (ew == 0 && lane == 0) PAIR_STAMP(tile_no, 3);
                                     },
                                     [&] {
                                         tc_fence_before();
                                         mbar_arrive_leader(&tempty_bar[as]);
+                                        if (ew == 0 && lane == 0) PAIR_STAMP(tile_no, 4);
                                     });
+            if (ew == 0 && lane == 0) PAIR_STAMP(tile_no, 5);
             if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
         }
         if (lane == 0) tma_store_wait_all<0>();
@@ -251,6 +295,15 @@ extern "C" void teo_dbg_pair_cfg(int group_m, int group_n, int raster, int l2_hi
     g_pair_cfg[2] = raster;
     g_pair_cfg[3] = l2_hint;
 }
+
+#ifdef TEO_PAIR_TRACE
+extern "C" int teo_dbg_pair_trace(void* device_buffer, int max_tiles) {
+    unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+    if (cudaMemcpyToSymbol(g_pair_trace, &p, sizeof(p)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(g_pair_trace_tiles, &max_tiles, sizeof(int)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
 
 // Called by launch_gemm with the tensor maps already built: ta = A boxes of 128 rows, tb = W boxes of 128 rows (or the
 // 4-D blocked map with one 128-row block per box), tc / tr = 32-row boxes of C and of the residual.
