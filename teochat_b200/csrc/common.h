@@ -111,6 +111,7 @@ struct teo_handle {
     bool pdl = true;                   // programmatic dependent launch inside teo_llama_decode_step (teo_set_pdl)
     bool decode_chain = true;          // teo_llama_decode_step uses the persistent chain kernel (teo_set_decode_chain; TEO_DEC_CHAIN=0)
     void* chain_sync = nullptr;        // 256 B of device memory: grid-barrier counters of the decode chain kernel (decode_chain.cu)
+    int* sk_flags = nullptr;           // 4 KiB of device memory: per-tile arrival counters of the stream-K GEMM's in-kernel reduction (gemm.cu)
     std::unordered_map<teo::TmapKey, CUtensorMap, teo::TmapKeyHash> tmaps;
 };
 
@@ -195,7 +196,15 @@ int launch_decode_chain(teo_handle* h, const ChainSpec* specs, int n_phases, int
                         float eps, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // Small-M (decode) GEMM that stops at the fp32 partials; the consumer kernel reduces them (fixed slot order).
+// With an SkFuse the GEMM reduces them itself: the CTA that holds slot 0 of a 128-row weight tile waits for the other slots'
+// arrival flags and runs the same reduction code as the stand-alone glue kernel on that tile (bit-identical results) — one kernel
+// and two grid-completion hand-offs less on the decode step's dependency chain.  kind 1: SwiGLU over interleaved gate/up rows.
+struct SkFuse {
+    int kind = 0;
+    bf16* out = nullptr;       // act [M, inter]
+    int inter = 0;
+};
 int launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                         size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked = 0);
+                         size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked = 0, const SkFuse* fuse = nullptr);
 
 }  // namespace teo

@@ -55,13 +55,15 @@ __device__ __forceinline__ float4 sum_partials4(const PartialInfo& pi, long long
 }
 
 // act[r, i] = bf16( silu(g) * u ),  g = bf16(Σ partials[r, i]),  u = bf16(Σ partials[r, inter + i]); thread `tid` of `nthreads`
-__device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* __restrict__ act, int rows, int inter, int interleaved,
-                                                   long long tid, long long nthreads) {
-    const int i4 = inter / 4;
+// (outputs [c_begin, c_begin + n_cols) of every row: the whole row for the stand-alone kernel, one 128-column weight tile = 64 outputs
+// for the stream-K GEMM's in-kernel fix-up)
+__device__ __forceinline__ void reduce_swiglu_cols(const PartialInfo& pi, bf16* __restrict__ act, int rows, int inter, int interleaved,
+                                                   int c_begin, int n_cols, long long tid, long long nthreads) {
+    const int i4 = n_cols / 4;
     const int up_off = interleaved ? 32 : inter;
     const long long total = static_cast<long long>(rows) * i4;
     for (long long i = tid; i < total; i += nthreads) {
-        const long long r = i / i4, c = (i % i4) * 4;
+        const long long r = i / i4, c = c_begin + (i % i4) * 4;
         const long long gc = gate_col(c, interleaved);
         // gate and up partials of the same slots are fetched together (one L2 round trip per four slots instead of two); each
         // element is still summed in the order s = 0,1,…
@@ -89,6 +91,10 @@ __device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* 
         }
         *reinterpret_cast<uint2*>(act + r * inter + c) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
     }
+}
+__device__ __forceinline__ void reduce_swiglu_part(const PartialInfo& pi, bf16* __restrict__ act, int rows, int inter, int interleaved,
+                                                   long long tid, long long nthreads) {
+    reduce_swiglu_cols(pi, act, rows, inter, interleaved, 0, inter, tid, nthreads);
 }
 
 // One warp per (sequence, head) — `gw` of n_seqs·n_heads: reduce the q/k/v partials, RoPE q and k, write q into the qkv buffer

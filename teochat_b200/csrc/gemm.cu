@@ -31,6 +31,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "decode_reduce.cuh"
 #include "gemm_common.cuh"
 #include "ptx.cuh"
 
@@ -84,6 +85,8 @@ struct Scheduler {
         return true;
     }
 };
+
+__device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 template <int BN, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -356,6 +359,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);
+                if constexpr (SK) {
+                    if (g.fuse) {
+                        // ---- in-kernel reduction of this weight tile (all eight epilogue warps).  Every slot's partial is in global
+                        // memory first (fixed summation order s = 0,1,… over the slots, like the glue kernel: same code, same bits);
+                        // slots > 0 then announce themselves, slot 0 — for a tile shared with other CTAs always this CTA's LAST work
+                        // item: its range ends inside the tile — waits for them and reduces.
+                        const int tile = m_blk * num_n + n_blk;
+                        const int et = static_cast<int>(threadIdx.x) - 128;
+                        __threadfence();
+                        named_bar_sync_epi();
+                        if (split != 0) {
+                            if (et == 0) atomicAdd(&g.sk_flags[tile], 1);
+                        } else {
+                            const PartialInfo pi{reinterpret_cast<const float*>(g.C), g.split_stride, total_kb, g.sk_q, static_cast<int>(gridDim.x)};
+                            const int others = partial_count(pi, tile * BM) - 1;
+                            if (others > 0) {
+                                if (et == 0) {
+                                    const long long t0 = clock64();
+                                    while (*reinterpret_cast<volatile int*>(&g.sk_flags[tile]) < others) {
+                                        if (clock64() - t0 > 8000000000LL) {
+                                            printf("teochat_b200: stream-K fix-up timed out (block %d tile %d)\n", blockIdx.x, tile);
+                                            __trap();
+                                        }
+                                    }
+                                    g.sk_flags[tile] = 0;              // ready for the next launch
+                                    __threadfence();
+                                }
+                                named_bar_sync_epi();
+                            }
+                            reduce_swiglu_cols(pi, g.fuse_out, g.N, g.fuse_inter, 1, tile * (BM / 2), BM / 2, et, EPI_WARPS * 32);
+                        }
+                    }
+                }
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
@@ -554,7 +590,7 @@ static int launch_cfg(teo_handle* h, const CUtensorMap& ta, const CUtensorMap& t
 // Small-M GEMM that stops at the fp32 split-K partials: P[s][M][N] in `workspace`, s < *splits_out.
 // The caller's next kernel reduces them (fused with its own work) in the fixed order s = 0,1,...
 int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* workspace,
-                              size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked) {
+                              size_t workspace_bytes, PartialInfo* info, cudaStream_t stream, int w_blocked, const SkFuse* fuse) {
     TEO_CHECK_ARG(h != nullptr && info != nullptr, "gemm_partials: null handle");
     TEO_CHECK_ARG(M > 0 && M <= 128 && N >= 256 && K > 0 && K % 8 == 0, "gemm_partials: needs 0 < M <= 128, N >= 256, K %% 8 == 0");
     const GemmPlan p = plan_gemm(M, N, K, h->num_sms);
@@ -576,6 +612,19 @@ int teo::launch_gemm_partials(teo_handle* h, const bf16* A, int lda, const bf16*
     g.C = workspace;
     g.ldc = N;
     g.split_stride = static_cast<long long>(M) * N;
+    if (fuse != nullptr && fuse->kind != 0) {
+        TEO_CHECK_ARG(fuse->kind == 1 && fuse->out && N == 2 * fuse->inter && fuse->inter % 64 == 0 && N % BM == 0 && N / BM <= 1024,
+                      "gemm_partials: the fused SwiGLU reduction needs interleaved gate/up rows, N = 2·inter, inter %% 64 == 0, ≤ 1024 tiles");
+        if (h->sk_flags == nullptr) {                 // (first call is the eager step that precedes graph capture)
+            TEO_CUDA(cudaMalloc(&h->sk_flags, 1024 * sizeof(int)));
+            TEO_CUDA(cudaMemset(h->sk_flags, 0, 1024 * sizeof(int)));
+        }
+        g.fuse = fuse->kind;
+        g.sk_flags = h->sk_flags;
+        g.fuse_out = fuse->out;
+        g.fuse_inter = fuse->inter;
+        g.fuse_interleaved = 1;
+    }
     CUtensorMap ta, tb;
     g.w_blocked = w_blocked ? 1 : 0;
     if (w_blocked) TEO_TRY(get_tmap_wblocked(h, W, N, K, 1, &ta));

@@ -66,6 +66,11 @@ struct GemmArgs {
     // … and the row statistics of the OUTPUT (the residual stream this GEMM writes) for the next folded LayerNorm:
     float* stats_out;           // f32 [M][stats_slots][2]; slot = 2·(column tile) + (column-chunk parity of the writing warp)
     int stats_slots;
+    // stream-K schedule: reduction of the partials + SwiGLU inside the GEMM (gemm.cu, launch_gemm_partials with an SkFuse)
+    int fuse;                   // 0 | 1: the CTA holding slot 0 of a weight tile reduces the tile's partials once the other slots have arrived
+    int* sk_flags;              // [tiles] arrival counters, zero between launches (reset by the reducing CTA)
+    bf16* fuse_out;             // act [batch, fuse_inter]
+    int fuse_inter, fuse_interleaved;
     unsigned long long* trace;  // development only (teo_dbg_gemm_trace): per CTA 8 %globaltimer stamps, else nullptr
 };
 

@@ -117,6 +117,7 @@ extern "C" int teo_create(int device_id, teo_handle** out) {
 }
 extern "C" int teo_destroy(teo_handle* h) {
     if (h && h->chain_sync) cudaFree(h->chain_sync);
+    if (h && h->sk_flags) cudaFree(h->sk_flags);
     delete h;
     return TEO_OK;
 }
@@ -481,6 +482,15 @@ extern "C" size_t teo_llama_decode_workspace_bytes(const teo_llama_model* m, int
     return decode_ws_layout(m, n_seqs, A, nullptr);
 }
 
+// In-kernel reduction of the decode gate/up GEMM (gemm.cu, SkFuse): TEO_SK_FUSE=0|1 (A/B measurements)
+static bool sk_fuse_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("TEO_SK_FUSE");
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
+}
+
 extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, void* next_ids, void* seq_lens, void* finished,
                                      void* tokens, int max_new, void* step_ptr, int n_seqs, int max_seq_len, const void* block_table,
                                      int max_pages, void* logits, int eos_id, void* workspace, size_t workspace_bytes, void* stream_) {
@@ -579,9 +589,20 @@ extern "C" int teo_llama_decode_step(teo_handle* h, const teo_llama_model* m, vo
             TEO_TRY(launch_reduce_residual_rmsnorm(pi, w.x, static_cast<const bf16*>(L.post_norm),
                                                    w.norm_out, n_seqs, hdim, m->eps, stream));
             // gate/up partials → reduce + SwiGLU
-            TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
-                                         w.gemm_ws_bytes, &pi, stream, m->w_blocked));
-            TEO_TRY(launch_reduce_swiglu(pi, w.act, n_seqs, I, m->gate_up_interleaved, stream));
+            if (sk_fuse_enabled() && m->gate_up_interleaved && I % 64 == 0) {
+                // … with the reduction + SwiGLU inside the GEMM (the CTA holding slot 0 of a weight tile reduces it)
+                SkFuse fz;
+                fz.kind = 1;
+                fz.out = w.act;
+                fz.inter = I;
+                TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
+                                             w.gemm_ws_bytes, &pi, stream, m->w_blocked, &fz));
+                h->launches -= 1;
+            } else {
+                TEO_TRY(launch_gemm_partials(h, w.norm_out, hdim, static_cast<const bf16*>(L.gate_up_w), hdim, n_seqs, 2 * I, hdim, w.gemm_ws,
+                                             w.gemm_ws_bytes, &pi, stream, m->w_blocked));
+                TEO_TRY(launch_reduce_swiglu(pi, w.act, n_seqs, I, m->gate_up_interleaved, stream));
+            }
             // down_proj partials → reduce + residual + the NEXT layer's input RMSNorm (or the final norm)
             TEO_TRY(launch_gemm_partials(h, w.act, I, static_cast<const bf16*>(L.down_w), I, n_seqs, hdim, I, w.gemm_ws, w.gemm_ws_bytes, &pi,
                                          stream, m->w_blocked));

@@ -493,6 +493,25 @@ def test_decode_chain_bit_identical_to_kernel_per_gemm(case):
     torch.cuda.empty_cache()
 
 
+def test_stream_k_fused_swiglu_reduction_is_bit_identical(tmp_path):
+    """TEO_SK_FUSE=1 (gemm.cu, SkFuse): the decode gate/up GEMM reduces its own stream-K partials and applies SwiGLU — the CTA holding slot 0
+    of a weight tile waits for the other slots' arrival flags and runs the glue kernel's reduction code on that tile — against the
+    stand-alone reduce_swiglu kernel: logits and ids BIT-identical, eager and graph-replayed (the switch is read once per process, so
+    each setting runs in its own process: tools/sk_fuse_check.py).  Optional path, measured 0.3-0.6 % slower (profiles/r02_sk_fuse.txt)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for f in ("0", "1"):
+        out = str(tmp_path / f"skf{f}.pt")
+        env = dict(os.environ, TEO_SK_FUSE=f)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "sk_fuse_check.py"), "dump", out], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        files.append(out)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sk_fuse_check.py"), "cmp", *files], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.count("BIT-IDENTICAL") == 4, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_vit_folded_layernorm_path_matches_default(monkeypatch):
     """The optional folded-LayerNorm ViT (TEO_VIT_LN_FOLD=1: teo_gemm_bf16_ex with gain-scaled weights, row statistics from the
     out-proj / fc2 epilogues, no LayerNorm kernels) against the default path and the fp32 oracle at full CLIP-L width."""
