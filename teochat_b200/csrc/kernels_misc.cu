@@ -165,7 +165,9 @@ __device__ __forceinline__ void store8(bf16* p, const float (&x)[8]) {
 // MODE 0: LayerNorm(x)            (x row = in[row])
 // MODE 1: ViT embeddings: x row = (tok==0 ? cls : patch_out[frame*np + tok-1]) + pos[tok], then LayerNorm
 // MODE 2: RMSNorm(x)
-template <int TPR, int MODE>
+// MAXV = 8-element vectors a thread may hold: 4 covers d ≤ 4·8·TPR (CLIP-L's 1024 at TPR 32, LLaMA-2-7B's 4096 at TPR 128) at half the
+// registers of the general 8 — more resident blocks, more bytes in flight on a kernel that does nothing but stream its rows.
+template <int TPR, int MODE, int MAXV>
 __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ b,
                             bf16* __restrict__ out, int rows, int d, float eps, const bf16* __restrict__ cls,
                             const bf16* __restrict__ pos, int n_patches) {
@@ -176,7 +178,7 @@ __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict_
     const int row = blockIdx.x * RPB + threadIdx.x / TPR;
     const int t = threadIdx.x % TPR;
     const bool active = row < rows;
-    float x[NORM_MAXV][8];
+    float x[MAXV][8];
     float sum = 0.f;
     const bf16* src = in;
     const bf16* posrow = nullptr;
@@ -190,7 +192,7 @@ __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict_
         }
     }
 #pragma unroll
-    for (int v = 0; v < NORM_MAXV; ++v) {
+    for (int v = 0; v < MAXV; ++v) {
         const int c = (v * TPR + t) * 8;
         if (active && c < d) {
             load8(src + c, x[v]);
@@ -215,7 +217,7 @@ __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict_
         mean = sum / static_cast<float>(d);
         float sq = 0.f;
 #pragma unroll
-        for (int v = 0; v < NORM_MAXV; ++v) {
+        for (int v = 0; v < MAXV; ++v) {
             const int c = (v * TPR + t) * 8;
             if (active && c < d) {
 #pragma unroll
@@ -228,7 +230,7 @@ __global__ void norm_kernel(const bf16* __restrict__ in, const bf16* __restrict_
     if (!active) return;
     bf16* dst = out + static_cast<size_t>(row) * d;
 #pragma unroll
-    for (int v = 0; v < NORM_MAXV; ++v) {
+    for (int v = 0; v < MAXV; ++v) {
         const int c = (v * TPR + t) * 8;
         if (c < d) {
             float wv[8], y[8];
@@ -253,9 +255,11 @@ static int launch_norm(const bf16* in, const bf16* w, const bf16* b, bf16* out, 
     TEO_CHECK_ARG(rows > 0 && d > 0 && d % 8 == 0, "norm: rows=%d d=%d (d must be a positive multiple of 8)", rows, d);
     TEO_CHECK_ARG(d <= 128 * 8 * NORM_MAXV, "norm: d=%d exceeds %d", d, 128 * 8 * NORM_MAXV);
     if (d <= 32 * 8 * 4) {
-        TEO_CUDA(launch_k(norm_kernel<32, MODE>, dim3((rows + 3) / 4), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
+        TEO_CUDA(launch_k(norm_kernel<32, MODE, 4>, dim3((rows + 3) / 4), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
+    } else if (d <= 128 * 8 * 4) {
+        TEO_CUDA(launch_k(norm_kernel<128, MODE, 4>, dim3(rows), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
     } else {
-        TEO_CUDA(launch_k(norm_kernel<128, MODE>, dim3(rows), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
+        TEO_CUDA(launch_k(norm_kernel<128, MODE, NORM_MAXV>, dim3(rows), dim3(128), 0, stream, in, w, b, out, rows, d, eps, cls, pos, n_patches));
     }
     TEO_LAUNCH_CHECK("norm_kernel");
     return TEO_OK;
